@@ -1,0 +1,95 @@
+"""Mint golden vectors from the REFERENCE's own Python (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports the reference from /root/reference through oracle/ref_shim.py (runtime
+shims only, nothing copied), runs it on seeded inputs and stores small
+input/output fixtures as ``tests/golden/*.npz``.  The GPU box has no
+/root/reference; tests there only read the committed fixtures.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+torch.set_num_threads(1)
+
+from oracle import model, ops, ref_shim  # noqa: E402
+from stereo_rcnn_b200.synth import synth_pair, gen_rois  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = ref_shim.load()
+    cfg = ref.cfg
+    calib = ref_shim.demo_calib()
+
+    # ---- (1) anchors + decode/clip --------------------------------------------------
+    shapes = [[150, 497], [75, 249], [38, 125], [19, 63], [10, 32]]
+    a = ref.generate_anchors.generate_anchors_all_pyramids(
+        np.array(cfg.FPN_ANCHOR_SCALES), cfg.ANCHOR_RATIOS, shapes,
+        np.array(cfg.FPN_FEAT_STRIDES), cfg.FPN_ANCHOR_STRIDE)
+    sel = np.random.RandomState(0).choice(a.shape[0], 4096, replace=False)
+    sel.sort()
+    deltas = (np.random.RandomState(1).randn(4096, 4) * 0.4).astype(np.float32)
+    an32 = torch.from_numpy(a[sel].astype(np.float32)).view(1, -1, 4)
+    dec = ref.bbox_transform.bbox_transform_inv(an32, torch.from_numpy(deltas).view(1, -1, 4), 1)
+    dec = ref.bbox_transform.clip_boxes(dec, torch.tensor([[600., 1987., 1.6]]), 1)[0].numpy()
+    np.savez_compressed(os.path.join(HERE, "anchors_decode.npz"), shapes=np.array(shapes),
+                        n_anchors=a.shape[0], sel=sel, anchors_sel=a[sel],
+                        anchors_sum=a.sum(0), anchors_abs_sum=np.abs(a).sum(0),
+                        deltas=deltas, decoded=dec)
+
+    # ---- (2) proposal layer on synthetic RPN outputs (small pyramid) ----------------
+    pshapes = [[40, 64], [20, 32], [10, 16], [5, 8], [3, 4]]
+    A = 3 * sum(h * w for h, w in pshapes)
+    rs = np.random.RandomState(7)
+    prob = rs.rand(1, A, 2).astype(np.float32)
+    # no forced score ties here: the reference leaves tie order to torch.sort (unspecified),
+    # so a golden can only pin tie-free inputs; the tie rule is covered by oracle-level tests.
+    bbox = (rs.randn(1, A, 6) * 0.3).astype(np.float32)
+    info = np.array([[160., 256., 1.0]], np.float32)
+    layer = ref.proposal_layer._ProposalLayer(cfg.FEAT_STRIDE[0], cfg.ANCHOR_RATIOS)
+    rl, rr = layer((torch.from_numpy(prob), torch.from_numpy(bbox), torch.from_numpy(info), "TEST", pshapes))
+    np.savez_compressed(os.path.join(HERE, "proposal_small.npz"), shapes=np.array(pshapes), cls_prob=prob,
+                        bbox_pred=bbox, im_info=info, rois_left=rl.numpy(), rois_right=rr.numpy())
+
+    # ---- (3) dense_align ------------------------------------------------------------
+    H, W = 600, 1987
+    left, right = synth_pair(H, W, seed=3, shift=40)
+    b, k, p = gen_rois(24, seed=3, p2=calib.p2)
+    scale = float(np.float32(1.6))
+    st, dis = ref.dense_align.align_parallel(calib, scale, torch.from_numpy(left)[None],
+                                             torch.from_numpy(right)[None], torch.from_numpy(b),
+                                             torch.from_numpy(k), torch.from_numpy(p))
+    s2 = scale * 2
+    uvz, wgt = ref.dense_align.sample(calib, s2, 2 * H, 2 * W, torch.from_numpy(b) * s2,
+                                      torch.from_numpy(p), (torch.from_numpy(k) * s2)[:, 3:5])
+    np.savez_compressed(os.path.join(HERE, "dense_align.npz"), H=H, W=W, seed=3, shift=40,
+                        p2=calib.p2, p3=calib.p3, scale=scale, box_left=b, keypoints=k, poses=p,
+                        status=st.numpy(), best_dis=dis.numpy(), npix=wgt.sum(1).numpy().astype(np.int32),
+                        uvz_head=uvz.numpy()[:, :64].copy())
+
+    # ---- (4) full forward on a small pair -------------------------------------------
+    sd = model.make_state_dict(3)
+    m = ref_shim.build_reference_model(sd)
+    H, W = 160, 256
+    left, right = synth_pair(H, W, seed=11, shift=7)
+    iml, imr = torch.from_numpy(left)[None], torch.from_numpy(right)[None]
+    info = torch.tensor([[H, W, 1.0]])
+    d = torch.zeros(1)
+    with torch.no_grad():
+        outs = m(iml, imr, info, d, d, d, d, d, d)
+    names = ["rois_left", "rois_right", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob",
+             "left_border_prob", "right_border_prob"]
+    gold = {n: o.numpy() for n, o in zip(names, outs[:8])}
+    np.savez_compressed(os.path.join(HERE, "forward_small.npz"), H=H, W=W, seed=11, shift=7,
+                        weight_seed=3, **gold)
+    print("goldens written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
