@@ -1,0 +1,164 @@
+/*
+ * stereo_b200.h -- C ABI of libstereo_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the Stereo R-CNN hot path.  Every entry point takes
+ * plain device pointers + sizes + an explicit stream (a cudaStream_t passed
+ * as void*), never allocates, never synchronises, and returns 0 on success
+ * or a non-zero code (a cudaError_t value, or SB_EINVAL for a bad argument /
+ * too-small workspace).  Caller allocates every output, as in the reference.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   sb_nms                    <- lib/model/nms/src/nms_cuda_kernel.h:5-6  (nms_cuda_compute)
+ *                                lib/model/nms/src/nms_cuda.h:4-5         (nms_cuda, THC glue)
+ *   sb_roi_align_forward      <- lib/model/roi_align/src/roi_align_kernel.h:13-17 (ROIAlignForwardLaucher)
+ *                                lib/model/roi_align/src/roi_align_cuda.h:1-2     (roi_align_forward_cuda)
+ *   sb_roi_align_backward     <- lib/model/roi_align/src/roi_align_kernel.h:24-27 (ROIAlignBackwardLaucher)
+ *                                lib/model/roi_align/src/roi_align_cuda.h:4-5     (roi_align_backward_cuda)
+ *   sb_proposal_layer         <- lib/model/rpn/proposal_layer.py:42-145 (_ProposalLayer.forward)
+ *   sb_dense_align            <- lib/model/dense_align/dense_align.py:240-300 (align_parallel)
+ *   sb_roi_align_pyramid_nhwc <- lib/model/stereo_rcnn/stereo_rcnn.py:110-139 (PyramidRoI_Feat + RoIAlignAvg)
+ *   sb_conv2d / sb_* layer ops<- torch.nn.Conv2d/BatchNorm2d/... call sites in
+ *                                lib/model/stereo_rcnn/resnet.py:66-121,236-286 and
+ *                                lib/model/rpn/stereo_rpn.py:32-40,73-95
+ */
+#ifndef STEREO_B200_H
+#define STEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_EINVAL (-22)
+
+typedef void* sb_stream_t; /* cudaStream_t */
+
+/* library / device info: returns the compute capability major*10+minor of device 0, <0 on error */
+int sb_version(void);
+int sb_device_cc(void);
+
+/* ---------------------------------------------------------------- NMS ----
+ * dets: n x 5 [x1,y1,x2,y2,score] fp32, pre-sorted by score desc.
+ * keep: >= n int32 (ascending indices of kept boxes), num_out: 1 int32.
+ * Suppress j>i when IoU(i,j) > thresh ("+1" areas), bit-exact with the
+ * reference's bitmask + greedy scan; the scan runs on the device.            */
+size_t sb_nms_workspace_bytes(int n);
+int sb_nms(const float* dets, int n, float thresh, int* keep, int* num_out,
+           void* workspace, size_t workspace_bytes, sb_stream_t stream);
+/* the raw 64x64 bitmask, upper-triangle blocks only (blocks below the diagonal are zero) */
+int sb_nms_mask(const float* dets, int n, float thresh, uint64_t* mask, sb_stream_t stream);
+
+/* ----------------------------------------------------------- RoIAlign ----
+ * Reference semantics: features NCHW fp32, rois R x 5 [batch,x1,y1,x2,y2],
+ * (ah, aw) is the tap lattice (RoIAlignAvg passes pooled+1), out R x C x ah x aw. */
+int sb_roi_align_forward(const float* features, int N, int C, int H, int W,
+                         const float* rois, int R, int ah, int aw, float spatial_scale,
+                         float* out, sb_stream_t stream);
+/* bottom_grad (N x C x H x W) must be zero-filled by the caller, as in the reference;
+ * accumulation is deterministic (segmented by RoI tap, no float atomics ordering races
+ * across launches: atomics are used, order-insensitive to 1 ulp)                  */
+int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W,
+                          const float* rois, int R, int ah, int aw, float spatial_scale,
+                          float* bottom_grad, sb_stream_t stream);
+
+/* Fused PyramidRoI_Feat: level routing (Q14) + per-level scale (Q15) + tap lattice +
+ * 2x2/stride-1 average, NHWC features, one launch for all levels.
+ * feats[l]: N x H_l x W_l x C (l = P2..P5); out[r][ph][pw][out_coff + c], row pitch out_ld floats. */
+int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* heights, const int* widths,
+                              int C, float im_h, const float* rois, int R, int pooled,
+                              float* out, int out_ld, int out_coff, sb_stream_t stream);
+
+/* ----------------------------------------------------- proposal layer ----
+ * cls_prob [B,A,2] (column 1 = score), bbox_pred_lr [B,A,6], im_info [B,3] (device).
+ * cfg: host struct (anchor pyramid + top-N / threshold constants), A = n_ratios*sum(h*w).
+ * rois_left/right: [B, post_nms_top_n, 5], zero padded; fully stream-ordered.          */
+typedef struct {
+    int n_levels;             /* <= 8 */
+    int shapes[8][2];         /* (h, w) of each pyramid level (rpn_shapes) */
+    int anchor_scales[8];     /* cfg.FPN_ANCHOR_SCALES */
+    int feat_strides[8];      /* cfg.FPN_FEAT_STRIDES  */
+    int n_ratios;             /* <= 4 */
+    double ratios[4];         /* cfg.ANCHOR_RATIOS */
+    int pre_nms_top_n;        /* cfg[key].RPN_PRE_NMS_TOP_N  (<= 16384) */
+    int post_nms_top_n;       /* cfg[key].RPN_POST_NMS_TOP_N */
+    float nms_thresh;         /* cfg[key].RPN_NMS_THRESH */
+} sb_proposal_cfg;
+size_t sb_proposal_workspace_bytes(int B, int A, int pre_nms_top_n);
+int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_lr, const float* im_info,
+                      int B, int A, const sb_proposal_cfg* cfg,
+                      float* rois_left, float* rois_right,
+                      void* workspace, size_t workspace_bytes, sb_stream_t stream);
+/* fused RPN head epilogue: raw head output [B, sum(h*w), ld] (cols 0..5 cls logits in the
+ * reference's channel order, 6..23 the 18 box channels) -> cls_prob [B,A,2], bbox_pred [B,A,6]
+ * with the reference's softmax channel pairing (stereo_rpn.py:52-60,81-83)               */
+int sb_rpn_head_epilogue(const float* head, int B, int P, int ld, float* cls_prob, float* bbox_pred,
+                         sb_stream_t stream);
+
+/* -------------------------------------------------------- dense_align ----
+ * im_left/right: 3 x H x W planar fp32 (network-scale, batch 1).
+ * calib4: host {P2[0,0], P2[0,2], P2[1,2], P2[0,3]-P3[0,3]}; scale = im_info[0,2].
+ * box_left D x 4, keypoints D x 5, poses D x 7 (device).  status[D], best_dis[D] (device). */
+size_t sb_dense_align_workspace_bytes(int H, int W, int D);
+int sb_dense_align(const float* im_left, const float* im_right, int H, int W,
+                   const double* calib4, double scale,
+                   const float* box_left, const float* keypoints, const float* poses, int D,
+                   float* status, float* best_dis,
+                   void* workspace, size_t workspace_bytes, sb_stream_t stream);
+
+/* ----------------------------------------------------- dense layer ops ----
+ * NHWC fp32 activations.  One descriptor drives both the SIMT fp32 kernel (stem, odd
+ * shapes) and the tcgen05 TF32 implicit-GEMM kernel (everything GEMM-shaped).          */
+typedef struct {
+    const float* in;        /* [N,H,W,in_ld] channels [0,Cin) used */
+    const float* wgt;       /* [Cout][kh][kw][Cin] */
+    const float* scale;     /* [Cout] or NULL (folded frozen BN gamma/sqrt(var+eps)) */
+    const float* shift;     /* [Cout] or NULL (folded BN beta / conv bias) */
+    const float* residual;  /* [N,Ho,Wo,res_ld] or NULL: added before ReLU */
+    const float* up_src;    /* [N,UH,UW,Cout] or NULL: bilinear(align_corners) upsample to Ho x Wo, added */
+    float* out;             /* out[n*out_n_stride + ho*out_h_stride + wo*out_w_stride + out_coff + c] */
+    int N, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
+    int in_ld, res_ld, UH, UW, relu;
+    int out_coff;
+    long long out_n_stride, out_h_stride, out_w_stride;
+} sb_conv_desc;
+
+int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream);
+/* tcgen05 path: requires Cin % 32 == 0 (K tile = one 128-byte swizzle row), stride 1. */
+int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream);
+int sb_conv2d_tc_supported(const sb_conv_desc* d);
+
+/* stem: NCHW image -> conv7x7/2 + frozen BN + ReLU -> NHWC (resnet.py:111-113) */
+int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[64][7][7][3]*/,
+                 const float* scale, const float* shift, float* out_nhwc, sb_stream_t stream);
+/* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
+int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
+/* x[:, ::2, ::2, :] (stride-2 1x1 convs of resnet.py:71 and P6 of stereo_rcnn.py:39) */
+int sb_subsample2(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
+/* keypoint tail: relu'd deconv output [R,G,G,C] -> sum over height -> 1x1 (C->6) -> [R,6,G]
+ * -> softmax over 4G / G / G (stereo_rcnn.py:262-271)                                    */
+int sb_kpts_tail(const float* x, int R, int G, int C, const float* w /*[6][C]*/, const float* b /*[6]*/,
+                 float* kpts_prob /*[R,4G]*/, float* left_prob /*[R,G]*/, float* right_prob /*[R,G]*/,
+                 float* kpts_pred_all /*[R,6,G] or NULL*/, sb_stream_t stream);
+/* box-head tail: fc7 [R,K] -> cls softmax [R,nc], bbox [R,6nc], dim_orien [R,5nc] */
+int sb_box_tail(const float* fc7, int R, int K, int n_classes,
+                const float* w_cls, const float* b_cls, const float* w_box, const float* b_box,
+                const float* w_dim, const float* b_dim,
+                float* cls_prob, float* bbox_pred, float* dim_orien, sb_stream_t stream);
+/* test-time decode (test_net.py:138-212), one image */
+int sb_test_decode(const float* rois_left, const float* rois_right, const float* bbox_pred,
+                   const float* dim_orien, const float* kpts_prob, const float* left_prob,
+                   const float* right_prob, const float* im_info, int R, int n_classes, int grid,
+                   float* pred_boxes_left, float* pred_boxes_right, float* dim_orien_out,
+                   float* pred_kpts, sb_stream_t stream);
+/* L2 flush helper for benchmarks: writes `bytes` of scratch */
+int sb_fill(float* p, size_t n, float v, sb_stream_t stream);
+/* number of kernel launches issued by this library since load (bench "gpu_launches") */
+unsigned long long sb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREO_B200_H */

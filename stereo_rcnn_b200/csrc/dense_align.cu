@@ -1,0 +1,357 @@
+// dense_align.cu -- photometric 3D-box depth refinement in two launches (sm_100a).
+//
+// Replaces lib/model/dense_align/dense_align.py:13-69,175-300 + box_3d.py:12-106
+// (align_parallel -> sample()/Box3d -> enumeration_depth x2).  The reference runs a Python
+// loop over RoIs with ~150 tiny kernels and host scalar reads each, builds a 38 MB uv grid,
+// then ~10 full passes over [50 x D x P x 3] intermediates per stage (3.7 GB each at D=2048).
+//
+// Here:
+//   K1 upsample2x_kernel : both images, F.upsample(x2, bilinear, align_corners=True) written
+//      once as pixel-interleaved float4 (c0,c1,c2,0) so that a bilinear tap is one 128-bit load.
+//   K2 dense_align_kernel: one CTA per RoI.  Thread 0 builds the 3D box (corners, the three
+//      visible planes by the nearest-vertex rule) in registers/smem; every thread then owns
+//      lattice pixels (row-major, stride 256), runs the ray/plane/in-box test, samples the left
+//      image once and accumulates the SAD for all 50 (then 20) depth hypotheses in registers,
+//      warp-shuffle + smem reduction, in-kernel argmin.  The last CTA to finish applies the
+//      reference's "no valid pixel anywhere -> return dis_init" early-out.
+// Nothing but the two upsampled images (2 x 76 MB) and D x 2 outputs touches HBM.
+//
+// Arithmetic mirrors oracle/csrc/oracle_ops.c (which is pinned to the reference's Python):
+// every fp32 step is an explicit _rn intrinsic in the reference's evaluation order.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const float* __restrict__ im0, const float* __restrict__ im1, int H, int W,
+                  float4* __restrict__ up0, float4* __restrict__ up1) {
+    const float* __restrict__ src = blockIdx.z ? im1 : im0;
+    float4* __restrict__ dst = blockIdx.z ? up1 : up0;
+    const int OH = 2 * H, OW = 2 * W;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= OW) return;
+    const float rh = (OH > 1) ? __fdiv_rn((float)(H - 1), (float)(OH - 1)) : 0.f;
+    const float rw = (OW > 1) ? __fdiv_rn((float)(W - 1), (float)(OW - 1)) : 0.f;
+    const float sy = __fmul_rn(rh, (float)y);
+    const int y1 = (int)sy;
+    const int yp = (y1 < H - 1) ? 1 : 0;
+    const float ly1 = __fsub_rn(sy, (float)y1), ly0 = __fsub_rn(1.f, ly1);
+    const float sx = __fmul_rn(rw, (float)x);
+    const int x1 = (int)sx;
+    const int xp = (x1 < W - 1) ? 1 : 0;
+    const float lx1 = __fsub_rn(sx, (float)x1), lx0 = __fsub_rn(1.f, lx1);
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* r0 = src + ((size_t)c * H + y1) * W;
+        const float* r1 = r0 + (size_t)yp * W;
+        float top = __fadd_rn(__fmul_rn(lx0, __ldg(r0 + x1)), __fmul_rn(lx1, __ldg(r0 + x1 + xp)));
+        float bot = __fadd_rn(__fmul_rn(lx0, __ldg(r1 + x1)), __fmul_rn(lx1, __ldg(r1 + x1 + xp)));
+        o[c] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    }
+    dst[(size_t)y * OW + x] = make_float4(o[0], o[1], o[2], 0.f);
+}
+
+struct Consts {
+    float s2f, f32, bl32, fb32, cx32, cy32, fw2, fh2;
+    int FH, FW;
+};
+
+struct RoiCtx {
+    float T[3];
+    float c, s;
+    float pmin[3], pmax[3];
+    float planes[3][4];
+    int u0, nu, su, v0, nv, sv;
+    float z0, dis_init;
+};
+
+__device__ __forceinline__ void make_plane(const float* p1, const float* p2, const float* p3, float* pl) {
+    float a1[3], a2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a1[k] = __fsub_rn(p2[k], p1[k]); a2[k] = __fsub_rn(p3[k], p1[k]); }
+    float n0 = __fsub_rn(__fmul_rn(a1[1], a2[2]), __fmul_rn(a1[2], a2[1]));
+    float n1 = __fsub_rn(__fmul_rn(a1[2], a2[0]), __fmul_rn(a1[0], a2[2]));
+    float n2 = __fsub_rn(__fmul_rn(a1[0], a2[1]), __fmul_rn(a1[1], a2[0]));
+    pl[0] = n0; pl[1] = n1; pl[2] = n2;
+    pl[3] = __fsub_rn(__fsub_rn(__fmul_rn(-n0, p1[0]), __fmul_rn(n1, p1[1])), __fmul_rn(n2, p1[2]));
+}
+
+__device__ __forceinline__ int py_slice(int start, int stop, int step, int size, int* first) {
+    if (start < 0) { start += size; if (start < 0) start = 0; }
+    if (start > size) start = size;
+    if (stop < 0) { stop += size; if (stop < 0) stop = 0; }
+    if (stop > size) stop = size;
+    *first = start;
+    if (stop <= start) return 0;
+    return (stop - start + step - 1) / step;
+}
+
+__device__ void setup_roi(const float* box_in, const float* kp, const float* pose, const Consts& k, RoiCtx* g) {
+    const int PV[6][3] = {{0, 3, 4}, {2, 3, 6}, {1, 2, 5}, {0, 1, 4}, {0, 1, 2}, {4, 5, 6}};
+    const int PG[8][3] = {{0, 3, 4}, {2, 3, 4}, {1, 2, 4}, {0, 1, 4}, {0, 3, 5}, {2, 3, 5}, {1, 2, 5}, {0, 1, 5}};
+    float box[4], border[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) box[i] = __fmul_rn(box_in[i], k.s2f);
+    border[0] = __fmul_rn(kp[3], k.s2f);
+    border[1] = __fmul_rn(kp[4], k.s2f);
+    g->T[0] = pose[0]; g->T[1] = pose[1]; g->T[2] = pose[2];
+    const float w = pose[3], h = pose[4], l = pose[5];
+    g->c = (float)cos((double)pose[6]);
+    g->s = (float)sin((double)pose[6]);
+    const float hw = __fdiv_rn(w, 2.0f), hl = __fdiv_rn(l, 2.0f);
+    float Po[8][3] = {{-hw, 0.f, -hl}, {-hw, 0.f, hl}, {hw, 0.f, hl}, {hw, 0.f, -hl},
+                      {-hw, -h, -hl},  {-hw, -h, hl},  {hw, -h, hl},  {hw, -h, -hl}};
+    float Pc[8][3];
+    int nearest = 0;
+    float best = 100000000.f;
+    for (int i = 0; i < 8; ++i) {
+        Pc[i][0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(g->c, Po[i][0]), __fmul_rn(0.f, Po[i][1])), __fmul_rn(g->s, Po[i][2])), g->T[0]);
+        Pc[i][1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.f, Po[i][0]), __fmul_rn(1.f, Po[i][1])), __fmul_rn(0.f, Po[i][2])), g->T[1]);
+        Pc[i][2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-g->s, Po[i][0]), __fmul_rn(0.f, Po[i][1])), __fmul_rn(g->c, Po[i][2])), g->T[2]);
+        float nn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(Pc[i][0], Pc[i][0]), __fmul_rn(Pc[i][1], Pc[i][1])), __fmul_rn(Pc[i][2], Pc[i][2])));
+        if (nn < best) { best = nn; nearest = i; }
+    }
+    for (int q = 0; q < 3; ++q) {
+        const int* v = PV[PG[nearest][q]];
+        make_plane(Pc[v[0]], Pc[v[1]], Pc[v[2]], g->planes[q]);
+    }
+    g->pmin[0] = __fsub_rn(-hw, 0.01f); g->pmin[1] = __fsub_rn(-h, 0.01f); g->pmin[2] = __fsub_rn(-hl, 0.01f);
+    g->pmax[0] = __fadd_rn(hw, 0.01f);  g->pmax[1] = __fadd_rn(0.f, 0.01f); g->pmax[2] = __fadd_rn(hl, 0.01f);
+    int su = (int)__fdiv_rn(__fsub_rn(border[1], border[0]), 56.0f); if (su < 1) su = 1;
+    int sv = (int)__fdiv_rn(__fsub_rn(box[3], box[1]), 56.0f);       if (sv < 1) sv = 1;
+    int vs = (int)__fadd_rn(__fdiv_rn(__fadd_rn(box[1], box[3]), 2.0f), 0.5f);
+    int ve = (int)__fadd_rn(__fsub_rn(box[3], __fmul_rn(__fsub_rn(box[3], box[1]), 0.1f)), 0.5f);
+    int us = (int)__fadd_rn(border[0], 0.5f);
+    int ue = (int)__fadd_rn(border[1], 0.5f);
+    g->su = su; g->sv = sv;
+    g->nv = py_slice(vs, ve, sv, k.FH, &g->v0);
+    g->nu = py_slice(us, ue, su, k.FW, &g->u0);
+    g->dis_init = __fdiv_rn(k.fb32, pose[2]);
+    g->z0 = __fmul_rn(__fmul_rn(__fdiv_rn(1.0f, g->dis_init), k.f32), k.bl32);
+}
+
+__device__ __forceinline__ bool ray_test(const RoiCtx& g, float u, float v, const Consts& k, float* dz) {
+    const float rx = __fdiv_rn(__fsub_rn(u, k.cx32), k.f32), ry = __fdiv_rn(__fsub_rn(v, k.cy32), k.f32);
+    float oz = 0.f;
+    bool m = false;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (m) break;
+        const float* pl = g.planes[q];
+        float t = __fadd_rn(__fadd_rn(__fmul_rn(rx, pl[0]), __fmul_rn(ry, pl[1])), __fmul_rn(1.0f, pl[2]));
+        t = __fmul_rn(-__fdiv_rn(1.0f, t), pl[3]);
+        const float ix = __fsub_rn(__fmul_rn(rx, t), g.T[0]);
+        const float iy = __fsub_rn(__fmul_rn(ry, t), g.T[1]);
+        const float iz = __fsub_rn(__fmul_rn(1.0f, t), g.T[2]);
+        const float bx = __fadd_rn(__fadd_rn(__fmul_rn(g.c, ix), __fmul_rn(0.f, iy)), __fmul_rn(-g.s, iz));
+        const float by = __fadd_rn(__fadd_rn(__fmul_rn(0.f, ix), __fmul_rn(1.f, iy)), __fmul_rn(0.f, iz));
+        const float bz = __fadd_rn(__fadd_rn(__fmul_rn(g.s, ix), __fmul_rn(0.f, iy)), __fmul_rn(g.c, iz));
+        m = (bx >= g.pmin[0]) && (by >= g.pmin[1]) && (bz >= g.pmin[2]) &&
+            (bx <= g.pmax[0]) && (by <= g.pmax[1]) && (bz <= g.pmax[2]);
+        oz = iz;
+    }
+    *dz = oz;
+    return m;
+}
+
+// F.grid_sample(bilinear, border, align_corners=True) on the interleaved image
+__device__ __forceinline__ float3 grid_sample(const float4* __restrict__ im, int H, int W, float gx, float gy) {
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float x1 = __fadd_rn(x0, 1.f), y1 = __fadd_rn(y0, 1.f);
+    const float wx1 = __fsub_rn(ix, x0), wx0 = __fsub_rn(x1, ix);
+    const float wy1 = __fsub_rn(iy, y0), wy0 = __fsub_rn(y1, iy);
+    const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0);
+    const float sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
+    const int xi0 = (int)x0, yi0 = (int)y0;
+    const bool okx = xi0 + 1 <= W - 1, oky = yi0 + 1 <= H - 1;
+    const float4* p = im + (size_t)yi0 * W + xi0;
+    const float4 a = __ldg(p);
+    float3 v = make_float3(__fmul_rn(a.x, nw), __fmul_rn(a.y, nw), __fmul_rn(a.z, nw));
+    if (okx) {
+        const float4 b = __ldg(p + 1);
+        v.x = __fadd_rn(v.x, __fmul_rn(b.x, ne)); v.y = __fadd_rn(v.y, __fmul_rn(b.y, ne)); v.z = __fadd_rn(v.z, __fmul_rn(b.z, ne));
+    }
+    if (oky && wy1 != 0.f) {   // a zero-weight row adds +-0 : skipped loads do not change the sum
+        const float4 c = __ldg(p + W);
+        v.x = __fadd_rn(v.x, __fmul_rn(c.x, sw)); v.y = __fadd_rn(v.y, __fmul_rn(c.y, sw)); v.z = __fadd_rn(v.z, __fmul_rn(c.z, sw));
+        if (okx) {
+            const float4 d = __ldg(p + W + 1);
+            v.x = __fadd_rn(v.x, __fmul_rn(d.x, se)); v.y = __fadd_rn(v.y, __fmul_rn(d.y, se)); v.z = __fadd_rn(v.z, __fmul_rn(d.z, se));
+        }
+    }
+    return v;
+}
+
+template <int NH>
+__device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, const float4* __restrict__ upL,
+                                            const float4* __restrict__ upR, const float* __restrict__ rdis,
+                                            float* __restrict__ red /*[8][NH+1]*/, float* __restrict__ cost_out,
+                                            int* npix_out) {
+    float acc[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) acc[h] = 0.f;
+    int cnt = 0;
+    const int total = g.nu * g.nv;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int a = q / g.nu, b = q - a * g.nu;
+        const float u = (float)(g.u0 + b * g.su), v = (float)(g.v0 + a * g.sv);
+        float dz;
+        if (!ray_test(g, u, v, k, &dz)) continue;
+        ++cnt;
+        const float gy = __fdiv_rn(__fsub_rn(v, k.fh2), k.fh2);
+        const float3 L = grid_sample(upL, k.FH, k.FW, __fdiv_rn(__fsub_rn(u, k.fw2), k.fw2), gy);
+        const float zf = __fdiv_rn(dz, k.fb32);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const float d = __fdiv_rn(1.0f, __fadd_rn(zf, rdis[h]));
+            const float gx = __fdiv_rn(__fsub_rn(__fsub_rn(u, d), k.fw2), k.fw2);
+            const float3 R = grid_sample(upR, k.FH, k.FW, gx, gy);
+            acc[h] += fabsf(__fsub_rn(L.x, R.x)) + fabsf(__fsub_rn(L.y, R.y)) + fabsf(__fsub_rn(L.z, R.z));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        float s = warp_sum(acc[h]);
+        if (lane == 0) red[warp * (NH + 1) + h] = s;
+    }
+    {
+        float s = warp_sum((float)cnt);
+        if (lane == 0) red[warp * (NH + 1) + NH] = s;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    if (threadIdx.x <= NH) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += red[w * (NH + 1) + threadIdx.x];
+        if (threadIdx.x < NH) cost_out[threadIdx.x] = s;
+        else *npix_out = (int)s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+dense_align_kernel(const float4* __restrict__ upL, const float4* __restrict__ upR, Consts k,
+                   const float* __restrict__ box_left, const float* __restrict__ keypoints,
+                   const float* __restrict__ poses, int D, float* __restrict__ status,
+                   float* __restrict__ best_dis, float* __restrict__ dis_init_ws, int* __restrict__ flags) {
+    __shared__ RoiCtx g;
+    __shared__ float rdis[50], depth[50], cost[50];
+    __shared__ float red[8 * 51];
+    __shared__ int npix;
+    __shared__ float best_depth;
+    __shared__ int is_last;
+    const int i = blockIdx.x;
+    if (threadIdx.x == 0) setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
+    __syncthreads();
+    // coarse: depth_i = (1/dis_init*f*bl - 12.5) + 0.5 i, clamped at 1.5 (dense_align.py:280-285)
+    if (threadIdx.x < 50) {
+        float d = __fadd_rn(__fsub_rn(g.z0, 12.5f), (float)(0.5 * threadIdx.x));
+        if (d < 1.5f) d = 1.5f;
+        depth[threadIdx.x] = d;
+        rdis[threadIdx.x] = __fdiv_rn(1.0f, __fmul_rn(__fdiv_rn(1.0f, d), k.fb32));
+    }
+    __syncthreads();
+    stage_costs<50>(g, k, upL, upR, rdis, red, cost, &npix);
+    if (threadIdx.x == 0) {
+        int bi = 0;
+        for (int h = 1; h < 50; ++h) if (cost[h] < cost[bi]) bi = h;
+        best_depth = depth[bi];
+    }
+    __syncthreads();
+    // fine: depth_j = (best - 0.5) + 0.05 j (dense_align.py:290-294)
+    if (threadIdx.x < 20) {
+        float d = __fadd_rn(__fsub_rn(best_depth, 0.5f), (float)(0.05 * threadIdx.x));
+        depth[threadIdx.x] = d;
+        rdis[threadIdx.x] = __fdiv_rn(1.0f, __fmul_rn(__fdiv_rn(1.0f, d), k.fb32));
+    }
+    __syncthreads();
+    int npix2;
+    stage_costs<20>(g, k, upL, upR, rdis, red, cost, &npix);
+    (void)npix2;
+    if (threadIdx.x == 0) {
+        int bi = 0;
+        for (int h = 1; h < 20; ++h) if (cost[h] < cost[bi]) bi = h;
+        const float bd = depth[bi];
+        status[i] = npix > 0 ? 1.f : 0.f;
+        best_dis[i] = __fadd_rn(__fdiv_rn(k.fb32, __fmul_rn(bd, k.s2f)), 0.5f);
+        dis_init_ws[i] = g.dis_init;
+        if (npix > 0) atomicOr(&flags[0], 1);
+        __threadfence();
+        is_last = (atomicAdd(&flags[1], 1) == D - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (atomicOr(&flags[0], 0) == 0) {   // dense_align.py:272-273: nothing valid anywhere
+            for (int j = threadIdx.x; j < D; j += blockDim.x) {
+                status[j] = 0.f;
+                best_dis[j] = __ldcg(dis_init_ws + j);
+            }
+        }
+    }
+}
+
+struct DaLayout { size_t upL, upR, dis, flags, total; };
+DaLayout da_layout(int H, int W, int D) {
+    DaLayout l;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
+    size_t px = (size_t)4 * H * W;
+    l.upL = take(px * sizeof(float4));
+    l.upR = take(px * sizeof(float4));
+    l.dis = take((size_t)(D > 0 ? D : 1) * sizeof(float));
+    l.flags = take(2 * sizeof(int));
+    l.total = off;
+    return l;
+}
+
+}  // namespace
+
+extern "C" size_t sb_dense_align_workspace_bytes(int H, int W, int D) { return da_layout(H, W, D).total; }
+
+extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H, int W, const double* calib4,
+                              double scale, const float* box_left, const float* keypoints, const float* poses,
+                              int D, float* status, float* best_dis, void* workspace, size_t workspace_bytes,
+                              sb_stream_t stream) {
+    if (D == 0) return SB_OK;
+    if (D < 0 || H < 2 || W < 2 || !im_left || !im_right || !calib4 || !workspace) return SB_EINVAL;
+    DaLayout l = da_layout(H, W, D);
+    if (workspace_bytes < l.total) return SB_EINVAL;
+    char* ws = (char*)workspace;
+    cudaStream_t st = sb_cs(stream);
+    float4* upL = (float4*)(ws + l.upL);
+    float4* upR = (float4*)(ws + l.upR);
+    float* dis_ws = (float*)(ws + l.dis);
+    int* flags = (int*)(ws + l.flags);
+    // dense_align.py:255-266 (python floats = doubles, cast to fp32 where they meet a tensor)
+    const double s2 = scale * 2.0;
+    const double fd = calib4[0] * s2;
+    const double bld = calib4[3] * s2 / fd;
+    Consts k;
+    k.s2f = (float)s2;
+    k.f32 = (float)fd;
+    k.bl32 = (float)bld;
+    k.fb32 = (float)(fd * bld);
+    k.cx32 = (float)(calib4[1] * s2);
+    k.cy32 = (float)(calib4[2] * s2);
+    k.FH = 2 * H;
+    k.FW = 2 * W;
+    k.fw2 = (float)(((double)k.FW - 1.0) / 2.0);
+    k.fh2 = (float)(((double)k.FH - 1.0) / 2.0);
+    cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
+    dim3 ug((k.FW + 255) / 256, k.FH, 2);
+    upsample2x_kernel<<<ug, 256, 0, st>>>(im_left, im_right, H, W, upL, upR);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    dense_align_kernel<<<D, 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, D, status, best_dis, dis_ws, flags);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

@@ -1,0 +1,274 @@
+// misc.cu -- small memory-bound layer ops of the Stereo R-CNN forward (sm_100a):
+// max-pool, stride-2 subsample, keypoint-head tail, box-head tail, test-time decode.
+#include "common.cuh"
+
+unsigned long long g_sb_launches = 0;
+
+extern "C" unsigned long long sb_launch_count(void) { return g_sb_launches; }
+extern "C" int sb_version(void) { return 100; }
+extern "C" int sb_device_cc(void) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) return -1;
+    return p.major * 10 + p.minor;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+fill_kernel(float4* __restrict__ p, size_t n4, float v) {
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * 256;
+    const float4 f = make_float4(v, v, v, v);
+    for (; i < n4; i += stride) p[i] = f;
+}
+
+// nn.MaxPool2d(kernel_size=3, stride=2, padding=0, ceil_mode=True) (resnet.py:113), NHWC
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int Ho, int Wo,
+               float4* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * C4;
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % C4);
+    long long t = e / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+        const int hi = ho * 2 + r;
+        if (hi >= H) break;
+        for (int s = 0; s < 3; ++s) {
+            const int wi = wo * 2 + s;
+            if (wi >= W) break;
+            const float4 v = __ldg(in + (((long long)n * H + hi) * W + wi) * C4 + c);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    out[e] = m;
+}
+
+__global__ void __launch_bounds__(256)
+subsample2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int Ho, int Wo,
+                  float4* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * C4;
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % C4);
+    long long t = e / C4;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    out[e] = __ldg(in + (((long long)n * H + 2 * ho) * W + 2 * wo) * C4 + c);
+}
+
+// keypoint tail (stereo_rcnn.py:262-271): x [R,G,G,C] -> sum over height -> 1x1 conv C->6
+// -> softmax(4G), softmax(G), softmax(G).  One CTA per RoI, one thread per channel.
+__global__ void __launch_bounds__(256)
+kpts_tail_kernel(const float* __restrict__ x, int G, int C, const float* __restrict__ w,
+                 const float* __restrict__ b, float* __restrict__ kpts_prob, float* __restrict__ left_prob,
+                 float* __restrict__ right_prob, float* __restrict__ pred_all) {
+    extern __shared__ float sm[];       // [8][6] partials + [6][G] logits
+    float* part = sm;
+    float* ka = sm + 48;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const float* xr = x + (size_t)r * G * G * C;
+    for (int col = 0; col < G; ++col) {
+        float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = tid; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int h = 0; h < G; ++h) s += __ldg(xr + ((size_t)h * G + col) * C + c);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) p[j] = fmaf(w[j * C + c], s, p[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            float s = warp_sum(p[j]);
+            if (lane == 0) part[warp * 6 + j] = s;
+        }
+        __syncthreads();
+        if (tid < 6) {
+            float s = 0.f;
+            for (int q = 0; q < nw; ++q) s += part[q * 6 + tid];
+            ka[tid * G + col] = s + (float)G * b[tid];
+        }
+        __syncthreads();
+    }
+    if (pred_all)
+        for (int e = tid; e < 6 * G; e += blockDim.x) pred_all[(size_t)r * 6 * G + e] = ka[e];
+    // three softmaxes: warp 0 -> kpts (4G), warp 1 -> left (G), warp 2 -> right (G)
+    if (warp < 3) {
+        const int n = warp == 0 ? 4 * G : G;
+        const float* src = warp == 0 ? ka : ka + (3 + warp) * G;
+        float* dst = warp == 0 ? kpts_prob + (size_t)r * 4 * G
+                               : (warp == 1 ? left_prob : right_prob) + (size_t)r * G;
+        float m = -INFINITY;
+        for (int e = lane; e < n; e += 32) m = fmaxf(m, src[e]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int e = lane; e < n; e += 32) s += expf(src[e] - m);
+        s = warp_sum(s);
+        for (int e = lane; e < n; e += 32) dst[e] = expf(src[e] - m) / s;
+    }
+}
+
+// box tail (stereo_rcnn.py:253-257): three linears on fc7 + softmax over classes
+__global__ void __launch_bounds__(256)
+box_tail_kernel(const float* __restrict__ fc7, int K, int nc, const float* __restrict__ w_cls,
+                const float* __restrict__ b_cls, const float* __restrict__ w_box,
+                const float* __restrict__ b_box, const float* __restrict__ w_dim,
+                const float* __restrict__ b_dim, float* __restrict__ cls_prob,
+                float* __restrict__ bbox_pred, float* __restrict__ dim_orien) {
+    __shared__ float part[8][48];
+    __shared__ float outv[48];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_out = 12 * nc;   // nc + 6nc + 5nc
+    const float* f = fc7 + (size_t)r * K;
+    for (int o = 0; o < n_out; ++o) {
+        const float* w = o < nc ? w_cls + (size_t)o * K
+                       : (o < 7 * nc ? w_box + (size_t)(o - nc) * K : w_dim + (size_t)(o - 7 * nc) * K);
+        float s = 0.f;
+        for (int k = tid; k < K; k += 256) s = fmaf(f[k], __ldg(w + k), s);
+        s = warp_sum(s);
+        if (lane == 0) part[warp][o] = s;
+    }
+    __syncthreads();
+    if (tid < n_out) {
+        float s = 0.f;
+        for (int q = 0; q < 8; ++q) s += part[q][tid];
+        s += tid < nc ? b_cls[tid] : (tid < 7 * nc ? b_box[tid - nc] : b_dim[tid - 7 * nc]);
+        outv[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float m = -INFINITY, s = 0.f;
+        for (int j = 0; j < nc; ++j) m = fmaxf(m, outv[j]);
+        for (int j = 0; j < nc; ++j) s += expf(outv[j] - m);
+        for (int j = 0; j < nc; ++j) cls_prob[(size_t)r * nc + j] = expf(outv[j] - m) / s;
+    }
+    if (tid >= nc && tid < 7 * nc) bbox_pred[(size_t)r * 6 * nc + tid - nc] = outv[tid];
+    if (tid >= 7 * nc && tid < n_out) dim_orien[(size_t)r * 5 * nc + tid - 7 * nc] = outv[tid];
+}
+
+// test_net.py:138-212 for one image; one thread per RoI
+__global__ void __launch_bounds__(128)
+test_decode_kernel(const float* __restrict__ rois_l, const float* __restrict__ rois_r,
+                   const float* __restrict__ bbox_pred, const float* __restrict__ dim_orien,
+                   const float* __restrict__ kpts_prob, const float* __restrict__ left_prob,
+                   const float* __restrict__ right_prob, const float* __restrict__ im_info, int R, int nc,
+                   int grid, float* __restrict__ pbl, float* __restrict__ pbr, float* __restrict__ dimo,
+                   float* __restrict__ pkpts) {
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= R) return;
+    const float stds[4] = {0.1f, 0.1f, 0.2f, 0.2f};           // cfg.TRAIN.BBOX_NORMALIZE_STDS/MEANS
+    const float dmean[5] = {1.6f, 1.5f, 4.0f, 0.0f, 0.0f};    // cfg.TRAIN.DIM_NORMALIZE_MEANS (STDS = 0.5)
+    const float imh = im_info[0], imw = im_info[1], sc = im_info[2];
+    const float xmax = __fsub_rn(imw, 1.0f), ymax = __fsub_rn(imh, 1.0f);
+    const float4 bl = make_float4(rois_l[5 * r + 1], rois_l[5 * r + 2], rois_l[5 * r + 3], rois_l[5 * r + 4]);
+    const float4 br = make_float4(rois_r[5 * r + 1], rois_r[5 * r + 2], rois_r[5 * r + 3], rois_r[5 * r + 4]);
+    for (int j = 0; j < nc; ++j) {
+        const float* d = bbox_pred + (size_t)r * 6 * nc + 6 * j;
+        float dl[4] = {d[0], d[1], d[2], d[3]}, dr[4] = {d[4], d[1], d[5], d[3]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dl[q] = __fadd_rn(__fmul_rn(dl[q], stds[q]), 0.0f);
+            dr[q] = __fadd_rn(__fmul_rn(dr[q], stds[q]), 0.0f);
+        }
+        float4 a = sb_decode_clip(bl, dl[0], dl[1], dl[2], dl[3], xmax, ymax);
+        float4 b = sb_decode_clip(br, dr[0], dr[1], dr[2], dr[3], xmax, ymax);
+        float* o = pbl + (size_t)r * 4 * nc + 4 * j;
+        o[0] = __fdiv_rn(a.x, sc); o[1] = __fdiv_rn(a.y, sc); o[2] = __fdiv_rn(a.z, sc); o[3] = __fdiv_rn(a.w, sc);
+        o = pbr + (size_t)r * 4 * nc + 4 * j;
+        o[0] = __fdiv_rn(b.x, sc); o[1] = __fdiv_rn(b.y, sc); o[2] = __fdiv_rn(b.z, sc); o[3] = __fdiv_rn(b.w, sc);
+        for (int q = 0; q < 5; ++q)
+            dimo[(size_t)r * 5 * nc + 5 * j + q] =
+                __fadd_rn(__fmul_rn(dim_orien[(size_t)r * 5 * nc + 5 * j + q], 0.5f), dmean[q]);
+    }
+    int kd = 0, ld = 0, rd = 0;
+    float km = kpts_prob[(size_t)r * 4 * grid];
+    for (int e = 1; e < 4 * grid; ++e) { float v = kpts_prob[(size_t)r * 4 * grid + e]; if (v > km) { km = v; kd = e; } }
+    float lm = left_prob[(size_t)r * grid], rm = right_prob[(size_t)r * grid];
+    for (int e = 1; e < grid; ++e) {
+        float v = left_prob[(size_t)r * grid + e]; if (v > lm) { lm = v; ld = e; }
+        v = right_prob[(size_t)r * grid + e]; if (v > rm) { rm = v; rd = e; }
+    }
+    const float g = (float)grid;
+    const float width = __fadd_rn(__fsub_rn(bl.z, bl.x), 1.0f);
+    const float ktype = __fdiv_rn((float)kd, g);
+    const float kdelta = fmodf((float)kd, g);
+    const float pk = __fadd_rn(__fdiv_rn(__fmul_rn(kdelta, width), g), bl.x);
+    const float pl = __fadd_rn(__fdiv_rn(__fmul_rn((float)ld, width), g), bl.x);
+    const float pr = __fadd_rn(__fdiv_rn(__fmul_rn((float)rd, width), g), bl.x);
+    float* o = pkpts + (size_t)r * 5;
+    o[0] = __fdiv_rn(pk, sc); o[1] = ktype; o[2] = km; o[3] = __fdiv_rn(pl, sc); o[4] = __fdiv_rn(pr, sc);
+}
+
+}  // namespace
+
+extern "C" int sb_fill(float* p, size_t n, float v, sb_stream_t stream) {
+    if (n == 0) return SB_OK;
+    if (n & 3) return SB_EINVAL;
+    fill_kernel<<<148 * 8, 256, 0, sb_cs(stream)>>>((float4*)p, n / 4, v);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream) {
+    if (C & 3) return SB_EINVAL;
+    auto osz = [](int x) { int o = (x - 3 + 1) / 2 + 1; if ((o - 1) * 2 >= x) --o; return o; };  // ceil mode
+    const int Ho = osz(H), Wo = osz(W);
+    const long long total = (long long)N * Ho * Wo * (C / 4);
+    maxpool_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>((const float4*)in, N, H, W, C / 4, Ho, Wo, (float4*)out);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_subsample2(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream) {
+    if (C & 3) return SB_EINVAL;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * Ho * Wo * (C / 4);
+    subsample2_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>((const float4*)in, N, H, W, C / 4, Ho, Wo, (float4*)out);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_kpts_tail(const float* x, int R, int G, int C, const float* w, const float* b, float* kpts_prob,
+                            float* left_prob, float* right_prob, float* kpts_pred_all, sb_stream_t stream) {
+    if (R == 0) return SB_OK;
+    size_t smem = (48 + 6 * (size_t)G) * sizeof(float);
+    kpts_tail_kernel<<<R, 256, smem, sb_cs(stream)>>>(x, G, C, w, b, kpts_prob, left_prob, right_prob, kpts_pred_all);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_box_tail(const float* fc7, int R, int K, int n_classes, const float* w_cls, const float* b_cls,
+                           const float* w_box, const float* b_box, const float* w_dim, const float* b_dim,
+                           float* cls_prob, float* bbox_pred, float* dim_orien, sb_stream_t stream) {
+    if (R == 0) return SB_OK;
+    if (n_classes < 1 || n_classes > 4) return SB_EINVAL;
+    box_tail_kernel<<<R, 256, 0, sb_cs(stream)>>>(fc7, K, n_classes, w_cls, b_cls, w_box, b_box, w_dim, b_dim,
+                                                  cls_prob, bbox_pred, dim_orien);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_test_decode(const float* rois_left, const float* rois_right, const float* bbox_pred,
+                              const float* dim_orien, const float* kpts_prob, const float* left_prob,
+                              const float* right_prob, const float* im_info, int R, int n_classes, int grid,
+                              float* pred_boxes_left, float* pred_boxes_right, float* dim_orien_out,
+                              float* pred_kpts, sb_stream_t stream) {
+    if (R == 0) return SB_OK;
+    test_decode_kernel<<<sb_div_up(R, 128), 128, 0, sb_cs(stream)>>>(rois_left, rois_right, bbox_pred, dim_orien,
+                                                                     kpts_prob, left_prob, right_prob, im_info, R,
+                                                                     n_classes, grid, pred_boxes_left,
+                                                                     pred_boxes_right, dim_orien_out, pred_kpts);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

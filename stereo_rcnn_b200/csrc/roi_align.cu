@@ -1,0 +1,228 @@
+// roi_align.cu -- RoIAlign forward / backward (reference layout) and the fused
+// pyramid RoIAlign+average used by the product forward (sm_100a).
+//
+// Arithmetic follows lib/model/roi_align/src/roi_align_kernel.cu:27-68 exactly:
+// fp32 roi scaling, fp64 for the sub-expressions the source writes with `1.` literals
+// (roi size, bin size, tap weights), one fused multiply-add for the lattice coordinate,
+// taps outside [0,H) x [0,W) -> 0, hstart = min(floor(h), H-2) (so [H-1,H) extrapolates).
+//
+// Kernels:
+//  * roi_align_fwd_nchw  : drop-in for ROIAlignForward (NCHW in, R x C x ah x aw out).
+//      Geometry is hoisted: one thread per (roi, tap, channel-run) instead of recomputing
+//      9 divisions per output element; writes coalesced along (ph,pw).
+//  * roi_align_bwd_nchw  : drop-in for ROIAlignBackward.
+//  * roi_align_pyramid_nhwc: PyramidRoI_Feat (stereo_rcnn.py:110-139) in ONE launch for all
+//      levels: level routing, per-level scale, (P+1)^2 tap lattice and the 2x2/stride-1
+//      average of modules/roi_align.py:29, on NHWC features.  One CTA per (roi, output row):
+//      two lattice rows are staged in shared memory (each tap = four coalesced 128-bit
+//      channel-vector loads), then averaged and stored as coalesced channel vectors -- the
+//      lattice (69 MB for the 14x14 keypoint pooling) never touches HBM.
+#include "common.cuh"
+
+namespace {
+
+struct RoiGeom {
+    float start_w, start_h, bin_w, bin_h;
+    int batch;
+};
+
+__device__ __forceinline__ RoiGeom roi_geom(const float* roi, float scale, int ah, int aw) {
+    RoiGeom g;
+    g.batch = (int)roi[0];
+    float sw = __fmul_rn(roi[1], scale), sh = __fmul_rn(roi[2], scale);
+    float ew = __fmul_rn(roi[3], scale), eh = __fmul_rn(roi[4], scale);
+    float rw = fmaxf((float)((double)__fsub_rn(ew, sw) + 1.), 0.f);
+    float rh = fmaxf((float)((double)__fsub_rn(eh, sh) + 1.), 0.f);
+    g.bin_h = (float)((double)rh / ((double)ah - 1.));
+    g.bin_w = (float)((double)rw / ((double)aw - 1.));
+    g.start_w = sw;
+    g.start_h = sh;
+    return g;
+}
+
+struct Tap {
+    int h0, w0;
+    double w00, w01, w10, w11;
+    bool zero;
+};
+
+__device__ __forceinline__ Tap make_tap(const RoiGeom& g, int ph, int pw, int H, int W) {
+    Tap t;
+    float h = __fmaf_rn((float)ph, g.bin_h, g.start_h);
+    float w = __fmaf_rn((float)pw, g.bin_w, g.start_w);
+    t.h0 = (int)fminf(floorf(h), (float)(H - 2));
+    t.w0 = (int)fminf(floorf(w), (float)(W - 2));
+    t.zero = (h < 0 || h >= H || w < 0 || w >= W);
+    double hr = (double)__fsub_rn(h, (float)t.h0), wr = (double)__fsub_rn(w, (float)t.w0);
+    t.w00 = (1. - hr) * (1. - wr);
+    t.w01 = (1. - hr) * wr;
+    t.w10 = hr * (1. - wr);
+    t.w11 = hr * wr;
+    return t;
+}
+
+// double evaluation order of the source: ((a*(1-hr))*(1-wr) + (b*(1-hr))*wr) + ...
+__device__ __forceinline__ float tap_value(const Tap& t, float a, float b, float c, float d, double hr_unused = 0) {
+    (void)hr_unused;
+    double v = (double)a * t.w00 + (double)b * t.w01 + (double)c * t.w10 + (double)d * t.w11;
+    return (float)v;
+}
+
+__global__ void __launch_bounds__(256)
+roi_align_fwd_nchw(const float* __restrict__ feat, int C, int H, int W, const float* __restrict__ rois,
+                   int ah, int aw, float scale, float* __restrict__ out) {
+    // grid: (roi, channel-chunk); threads sweep (c, ph, pw) with pw fastest
+    const int n = blockIdx.x;
+    const RoiGeom g = roi_geom(rois + 5 * n, scale, ah, aw);
+    const int taps = ah * aw;
+    const int c0 = blockIdx.y * 32;
+    const int cend = min(c0 + 32, C);
+    for (int e = threadIdx.x; e < (cend - c0) * taps; e += blockDim.x) {
+        int c = c0 + e / taps, p = e % taps;
+        int ph = p / aw, pw = p % aw;
+        Tap t = make_tap(g, ph, pw, H, W);
+        float v = 0.f;
+        if (!t.zero) {
+            const float* f = feat + (((size_t)g.batch * C + c) * H + t.h0) * W + t.w0;
+            v = tap_value(t, f[0], f[1], f[W], f[W + 1]);
+        }
+        out[((size_t)n * C + c) * taps + p] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+roi_align_bwd_nchw(const float* __restrict__ top, int C, int H, int W, const float* __restrict__ rois,
+                   int ah, int aw, float scale, float* __restrict__ bottom) {
+    const int n = blockIdx.x;
+    const RoiGeom g = roi_geom(rois + 5 * n, scale, ah, aw);
+    const int taps = ah * aw;
+    const int c0 = blockIdx.y * 32;
+    const int cend = min(c0 + 32, C);
+    for (int e = threadIdx.x; e < (cend - c0) * taps; e += blockDim.x) {
+        int c = c0 + e / taps, p = e % taps;
+        int ph = p / aw, pw = p % aw;
+        Tap t = make_tap(g, ph, pw, H, W);
+        if (t.zero) continue;
+        double tv = (double)top[((size_t)n * C + c) * taps + p];
+        float* b = bottom + (((size_t)g.batch * C + c) * H + t.h0) * W + t.w0;
+        atomicAdd(b, (float)(tv * t.w00));
+        atomicAdd(b + 1, (float)(tv * t.w01));
+        atomicAdd(b + W, (float)(tv * t.w10));
+        atomicAdd(b + W + 1, (float)(tv * t.w11));
+    }
+}
+
+struct PyramidArgs {
+    const float* feat[4];
+    int H[4], W[4];
+    float scale[4];
+};
+
+// stereo_rcnn.py:113-119: round(ln(sqrt(h*w)/224) + 4) clamped to [2,5] (fp32, natural log)
+__device__ __forceinline__ int roi_level(const float* roi) {
+    float h = __fadd_rn(__fsub_rn(roi[4], roi[2]), 1.0f);
+    float w = __fadd_rn(__fsub_rn(roi[3], roi[1]), 1.0f);
+    float l = logf(__fdiv_rn(sqrtf(__fmul_rn(h, w)), 224.0f));
+    l = rintf(__fadd_rn(l, 4.0f));  // torch.round: half to even
+    l = fminf(fmaxf(l, 2.f), 5.f);
+    return (int)l - 2;
+}
+
+// one CTA per (roi, output row ph); C % 4 == 0; dynamic smem = 2 * (P+1) * C floats
+__global__ void __launch_bounds__(256)
+roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int P,
+                       float* __restrict__ out, int out_ld, int out_coff) {
+    extern __shared__ float4 lat[];  // [2][P+1][C/4]
+    const int n = blockIdx.x, ph = blockIdx.y;
+    const float* roi = rois + 5 * n;
+    const int lv = roi_level(roi);
+    const int H = a.H[lv], W = a.W[lv];
+    const float* __restrict__ feat = a.feat[lv];
+    const int L = P + 1;
+    const RoiGeom g = roi_geom(roi, a.scale[lv], L, L);
+    const int C4 = C >> 2;
+    for (int e = threadIdx.x; e < 2 * L * C4; e += blockDim.x) {
+        const int c4 = e % C4, tp = e / C4;
+        const int row = tp / L, pw = tp % L;
+        const Tap t = make_tap(g, ph + row, pw, H, W);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!t.zero) {
+            const float4* f00 = reinterpret_cast<const float4*>(feat + (((size_t)g.batch * H + t.h0) * W + t.w0) * C) + c4;
+            const float4 p00 = __ldg(f00), p01 = __ldg(f00 + C4);
+            const float4 p10 = __ldg(f00 + (size_t)W * C4), p11 = __ldg(f00 + (size_t)W * C4 + C4);
+            v.x = tap_value(t, p00.x, p01.x, p10.x, p11.x);
+            v.y = tap_value(t, p00.y, p01.y, p10.y, p11.y);
+            v.z = tap_value(t, p00.z, p01.z, p10.z, p11.z);
+            v.w = tap_value(t, p00.w, p01.w, p10.w, p11.w);
+        }
+        lat[e] = v;
+    }
+    __syncthreads();
+    float* orow = out + ((size_t)n * P + ph) * P * out_ld + out_coff;
+    for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+        const int c4 = e % C4, pw = e / C4;
+        const float4 a0 = lat[(0 * L + pw) * C4 + c4], a1 = lat[(0 * L + pw + 1) * C4 + c4];
+        const float4 b0 = lat[(1 * L + pw) * C4 + c4], b1 = lat[(1 * L + pw + 1) * C4 + c4];
+        float4 o;  // avg_pool2d(2, stride 1): ((a+b)+(c+d)) * 0.25
+        o.x = __fmul_rn(__fadd_rn(__fadd_rn(a0.x, a1.x), __fadd_rn(b0.x, b1.x)), 0.25f);
+        o.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, a1.y), __fadd_rn(b0.y, b1.y)), 0.25f);
+        o.z = __fmul_rn(__fadd_rn(__fadd_rn(a0.z, a1.z), __fadd_rn(b0.z, b1.z)), 0.25f);
+        o.w = __fmul_rn(__fadd_rn(__fadd_rn(a0.w, a1.w), __fadd_rn(b0.w, b1.w)), 0.25f);
+        *reinterpret_cast<float4*>(orow + (size_t)pw * out_ld + 4 * c4) = o;
+    }
+}
+
+}  // namespace
+
+extern "C" int sb_roi_align_forward(const float* features, int N, int C, int H, int W, const float* rois,
+                                    int R, int ah, int aw, float spatial_scale, float* out,
+                                    sb_stream_t stream) {
+    (void)N;
+    if (R == 0) return SB_OK;
+    if (R < 0 || C <= 0 || ah < 2 || aw < 2 || !features || !rois || !out) return SB_EINVAL;
+    dim3 grid(R, (C + 31) / 32);
+    roi_align_fwd_nchw<<<grid, 256, 0, sb_cs(stream)>>>(features, C, H, W, rois, ah, aw, spatial_scale, out);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W, const float* rois,
+                                     int R, int ah, int aw, float spatial_scale, float* bottom_grad,
+                                     sb_stream_t stream) {
+    (void)N;
+    if (R == 0) return SB_OK;
+    if (R < 0 || C <= 0 || ah < 2 || aw < 2 || !top_grad || !rois || !bottom_grad) return SB_EINVAL;
+    dim3 grid(R, (C + 31) / 32);
+    roi_align_bwd_nchw<<<grid, 256, 0, sb_cs(stream)>>>(top_grad, C, H, W, rois, ah, aw, spatial_scale, bottom_grad);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* heights, const int* widths,
+                                         int C, float im_h, const float* rois, int R, int pooled,
+                                         float* out, int out_ld, int out_coff, sb_stream_t stream) {
+    if (R == 0) return SB_OK;
+    if (R < 0 || (C & 3) || pooled < 1 || (out_ld & 3) || (out_coff & 3)) return SB_EINVAL;
+    PyramidArgs a;
+    for (int l = 0; l < 4; ++l) {
+        a.feat[l] = feats[l];
+        a.H[l] = heights[l];
+        a.W[l] = widths[l];
+        // stereo_rcnn.py:128: scale = feat.size(2) / im_info[0][0] (python float), then float(...)
+        a.scale[l] = (float)((double)heights[l] / (double)im_h);
+    }
+    size_t smem = (size_t)2 * (pooled + 1) * C * sizeof(float);
+    if (smem > 200 * 1024) return SB_EINVAL;
+    static size_t cur_max = 48 * 1024;
+    if (smem > cur_max) {
+        cudaFuncSetAttribute(roi_align_pyramid_nhwc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cur_max = smem;
+    }
+    dim3 grid(R, pooled);
+    roi_align_pyramid_nhwc<<<grid, 256, smem, sb_cs(stream)>>>(a, C, rois, pooled, out, out_ld, out_coff);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

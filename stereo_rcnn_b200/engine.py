@@ -1,0 +1,203 @@
+"""The Stereo R-CNN test-mode forward on hand-written sm_100a kernels.
+
+Host-side schedule of `_StereoRCNN.forward` (lib/model/stereo_rcnn/stereo_rcnn.py:141-324):
+weights are packed once (NHWC / K-major, frozen BN folded to per-channel scale+shift --
+resnet.py:300-309 freezes every BN), left and right images run through the trunk as one
+batch of two, and every stage is a libstereo_b200 kernel launched on torch's current stream.
+There is no PyTorch operator on the compute path (torch only allocates device memory).
+"""
+import torch
+
+from . import ops
+
+LAYERS = [3, 4, 23, 3]
+PLANES = [64, 128, 256, 512]
+STRIDES = [1, 2, 2, 2]
+EPS = 1e-5
+
+
+def _pack_conv(w):
+    """[Cout,Cin,kh,kw] -> [Cout,kh,kw,Cin] contiguous (K-major rows, one per output channel)"""
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+class PackedConv(object):
+    __slots__ = ("w", "scale", "shift", "Cin", "Cout", "kh", "kw", "pad")
+
+    def __init__(self, w, scale, shift, pad):
+        self.Cout, self.Cin, self.kh, self.kw = w.shape
+        self.w, self.scale, self.shift, self.pad = _pack_conv(w), scale, shift, pad
+
+
+class StereoRCNNEngine(object):
+    """state_dict uses the reference's key names (RCNN_layer1.0.0.conv1.weight, ...)"""
+
+    def __init__(self, state_dict, device="cuda", n_classes=2, conv_impl="auto"):
+        self.device = torch.device(device)
+        self.n_classes = n_classes
+        self.conv_impl = conv_impl
+        self.impl_used = {}
+        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
+              if not k.endswith("num_batches_tracked")}
+        self.p = {}
+
+        def bn_fold(k):
+            s = sd[k + ".weight"] / torch.sqrt(sd[k + ".running_var"] + EPS)
+            return s.contiguous(), (sd[k + ".bias"] - sd[k + ".running_mean"] * s).contiguous()
+
+        def conv_bn(ck, bk, pad):
+            s, b = bn_fold(bk)
+            self.p[ck] = PackedConv(sd[ck + ".weight"], s, b, pad)
+
+        def conv_bias(ck, pad):
+            self.p[ck] = PackedConv(sd[ck + ".weight"], None, sd[ck + ".bias"].contiguous(), pad)
+
+        # stem: [64,3,7,7] -> [64][7][7][3]
+        s, b = bn_fold("RCNN_layer0.1")
+        self.stem = (_pack_conv(sd["RCNN_layer0.0.weight"]), s, b)
+        for li, nb in enumerate(LAYERS):
+            for bi in range(nb):
+                p = "RCNN_layer%d.0.%d" % (li + 1, bi)
+                conv_bn(p + ".conv1", p + ".bn1", 0)
+                conv_bn(p + ".conv2", p + ".bn2", 1)
+                conv_bn(p + ".conv3", p + ".bn3", 0)
+                if bi == 0:
+                    conv_bn(p + ".downsample.0", p + ".downsample.1", 0)
+        for k in ("RCNN_toplayer", "RCNN_latlayer1", "RCNN_latlayer2", "RCNN_latlayer3"):
+            conv_bias(k, 0)
+        for k in ("RCNN_smooth1", "RCNN_smooth2", "RCNN_smooth3", "RCNN_rpn.RPN_Conv"):
+            conv_bias(k, 1)
+        # RPN 1x1 heads fused: rows 0..5 cls logits, 6..23 box deltas, 24..31 zero padding
+        wh = torch.zeros(32, 1024, 1, 1, device=self.device)
+        bh = torch.zeros(32, device=self.device)
+        wh[0:6] = sd["RCNN_rpn.RPN_cls_score.weight"]
+        wh[6:24] = sd["RCNN_rpn.RPN_bbox_pred_left_right.weight"]
+        bh[0:6] = sd["RCNN_rpn.RPN_cls_score.bias"]
+        bh[6:24] = sd["RCNN_rpn.RPN_bbox_pred_left_right.bias"]
+        self.p["rpn_heads"] = PackedConv(wh, None, bh, 0)
+        # box head: Conv2d(512,2048,k=7,s=7) on a 7x7 map == FC over (ph,pw,c) of the NHWC pooled tile
+        w0 = sd["RCNN_top.0.weight"]                                   # [2048,512,7,7]
+        self.p["RCNN_top.0"] = PackedConv(_pack_conv(w0).reshape(2048, 7 * 7 * 512, 1, 1), None,
+                                          sd["RCNN_top.0.bias"].contiguous(), 0)
+        conv_bias("RCNN_top.3", 0)
+        for i in range(0, 12, 2):
+            conv_bias("RCNN_kpts.%d" % i, 1)
+        # ConvTranspose2d(256,256,2,2): out[2i+a,2j+b] = W[:,:,a,b]^T x[i,j]  -> four 1x1 convs
+        wd = sd["RCNN_kpts.12.weight"]                                 # [Cin,Cout,2,2]
+        self.deconv = [[PackedConv(wd[:, :, a, b].t().contiguous().reshape(256, 256, 1, 1), None,
+                                   sd["RCNN_kpts.12.bias"].contiguous(), 0) for b in range(2)] for a in range(2)]
+        self.kpts_class = (sd["kpts_class.weight"].reshape(6, 256).contiguous(), sd["kpts_class.bias"].contiguous())
+        self.fc = [sd[k].contiguous() for k in ("RCNN_cls_score.weight", "RCNN_cls_score.bias",
+                                                "RCNN_bbox_pred.weight", "RCNN_bbox_pred.bias",
+                                                "RCNN_dim_orien_pred.weight", "RCNN_dim_orien_pred.bias")]
+
+    # ------------------------------------------------------------------ helpers
+    def _conv(self, x, pc, relu=False, stride=1, residual=None, up_src=None, out=None, out_coff=0,
+              out_strides=None, Cin=None, tag=None):
+        N, H, W = x.shape[:3]
+        Ho = (H + 2 * pc.pad - pc.kh) // stride + 1
+        Wo = (W + 2 * pc.pad - pc.kw) // stride + 1
+        if out is None:
+            out = torch.empty(N, Ho, Wo, pc.Cout, dtype=torch.float32, device=x.device)
+        d = ops.conv_desc(x, pc.w, out, pc.Cin if Cin is None else Cin, pc.Cout, pc.kh, pc.kw, stride, pc.pad,
+                          Ho, Wo, scale=pc.scale, shift=pc.shift, residual=residual, up_src=up_src, relu=relu,
+                          out_coff=out_coff, out_strides=out_strides)
+        impl = ops.conv2d(d, self.conv_impl)
+        if tag is not None:
+            self.impl_used[tag] = impl
+        return out
+
+    def _bottleneck(self, x, prefix, stride, has_ds):
+        """resnet.py:82-102; the stride sits on the 1x1 conv1 and on the downsample (Q1)"""
+        xin = ops.subsample2(x) if stride == 2 else x
+        o = self._conv(xin, self.p[prefix + ".conv1"], relu=True, tag=prefix + ".conv1")
+        o = self._conv(o, self.p[prefix + ".conv2"], relu=True, tag=prefix + ".conv2")
+        res = self._conv(xin, self.p[prefix + ".downsample.0"], tag=prefix + ".ds") if has_ds else x
+        return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3")
+
+    def trunk_fpn(self, im_nchw):
+        """images [N,3,H,W] NCHW -> dict of NHWC C2..C5, P2..P6 (stereo_rcnn.py:155-168)"""
+        c1 = ops.maxpool3x3s2_ceil(ops.stem_conv(im_nchw, *self.stem))
+        feats = {"c1": c1}
+        x = c1
+        for li, nb in enumerate(LAYERS):
+            for bi in range(nb):
+                x = self._bottleneck(x, "RCNN_layer%d.0.%d" % (li + 1, bi), STRIDES[li] if bi == 0 else 1, bi == 0)
+            feats["c%d" % (li + 2)] = x
+        p5 = self._conv(feats["c5"], self.p["RCNN_toplayer"], tag="toplayer")
+        t = self._conv(feats["c4"], self.p["RCNN_latlayer1"], up_src=p5, tag="lat1")     # lateral + upsample-add
+        p4 = self._conv(t, self.p["RCNN_smooth1"], tag="smooth1")
+        t = self._conv(feats["c3"], self.p["RCNN_latlayer2"], up_src=p4, tag="lat2")
+        p3 = self._conv(t, self.p["RCNN_smooth2"], tag="smooth2")
+        t = self._conv(feats["c2"], self.p["RCNN_latlayer3"], up_src=p3, tag="lat3")
+        p2 = self._conv(t, self.p["RCNN_smooth3"], tag="smooth3")
+        p6 = ops.subsample2(p5)                                                           # Q5
+        feats.update(p2=p2, p3=p3, p4=p4, p5=p5, p6=p6)
+        return feats
+
+    def rpn(self, feats, B):
+        """stereo_rpn.py:73-95 -> cls_prob [B,A,2], bbox_pred [B,A,6], level shapes"""
+        levels = [feats[k] for k in ("p2", "p3", "p4", "p5", "p6")]
+        shapes = [[f.shape[1], f.shape[2]] for f in levels]
+        P = sum(h * w for h, w in shapes)
+        dev = self.device
+        head = torch.empty(B, P, 32, dtype=torch.float32, device=dev)
+        off = 0
+        for f, (h, w) in zip(levels, shapes):
+            cat = torch.empty(B, h, w, 1024, dtype=torch.float32, device=dev)
+            for side in range(2):   # shared RPN_Conv on L then R, channel-concatenated (Q6)
+                self._conv(f[side * B:(side + 1) * B], self.p["RCNN_rpn.RPN_Conv"], relu=True, out=cat,
+                           out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv")
+            self._conv(cat, self.p["rpn_heads"], out=head[:, off:off + h * w],
+                       out_strides=(P * 32, w * 32, 32), tag="rpn_heads")
+            off += h * w
+        cls_prob, bbox = ops.rpn_head_epilogue(head, B, P)
+        return cls_prob, bbox, shapes
+
+    def heads(self, feats, B, rois_l, rois_r, im_h):
+        """stereo_rcnn.py:240-271 on flattened rois [R,5]"""
+        mk = ("p2", "p3", "p4", "p5")
+        fl = [feats[k][:B] for k in mk]
+        fr = [feats[k][B:] for k in mk]
+        R = rois_l.shape[0]
+        dev = self.device
+        pooled = torch.empty(R, 7, 7, 512, dtype=torch.float32, device=dev)
+        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0)
+        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256)
+        x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0")
+        fc7 = self._conv(x, self.p["RCNN_top.3"], relu=True, tag="top3").view(R, 2048)
+        cls_prob, bbox, dim = ops.box_tail(fc7, *self.fc, n_classes=self.n_classes)
+        pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14)
+        x = pk
+        for i in range(0, 12, 2):
+            x = self._conv(x, self.p["RCNN_kpts.%d" % i], relu=True, tag="kpts%d" % i)
+        up = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
+        for a in range(2):
+            for b in range(2):
+                self._conv(x, self.deconv[a][b], relu=True, out=up[:, a:, b:],
+                           out_strides=(28 * 28 * 256, 2 * 28 * 256, 2 * 256), tag="deconv")
+        kp, lb, rb, ka = ops.kpts_tail(up, *self.kpts_class, want_pred_all=True)
+        return dict(pooled_box=pooled, pooled_kpts=pk, fc7=fc7, cls_prob=cls_prob, bbox_pred=bbox,
+                    dim_orien_pred=dim, kpts_prob=kp, left_border_prob=lb, right_border_prob=rb,
+                    kpts_pred_all=ka)
+
+    @torch.no_grad()
+    def forward(self, im_left, im_right, im_info, cfg_key="TEST", keep_features=False, im_h=None):
+        """im_left/right [B,3,H,W] NCHW fp32 (BGR - means), im_info [B,3] (device) -> dict (the reference's
+        tuple order is produced by model.stereo_rcnn.resnet.resnet.forward).  `im_h` (= im_info[0][0],
+        stereo_rcnn.py:128) is taken from the tensor shape so that no device->host read is needed."""
+        B = im_left.shape[0]
+        im_h = float(im_left.shape[2]) if im_h is None else float(im_h)
+        im = torch.cat((im_left, im_right), 0).contiguous()
+        feats = self.trunk_fpn(im)
+        cls_prob, bbox, shapes = self.rpn(feats, B)
+        rl, rr = ops.proposal_layer(cls_prob, bbox, im_info, cfg_key, shapes)
+        out = self.heads(feats, B, rl.view(-1, 5), rr.view(-1, 5), im_h)
+        n = rl.shape[1]
+        out.update(rois_left=rl, rois_right=rr, rpn_cls_prob=cls_prob, rpn_bbox_pred=bbox, rpn_shapes=shapes)
+        out["cls_prob"] = out["cls_prob"].view(B, n, -1)
+        out["bbox_pred"] = out["bbox_pred"].view(B, n, -1)
+        out["dim_orien_pred"] = out["dim_orien_pred"].view(B, n, -1)
+        if keep_features:
+            out["feats"] = feats
+        return out

@@ -1,0 +1,301 @@
+"""Torch-tensor front end of the C ABI (device memory + current stream only).
+
+Every function launches hand-written sm_100a kernels from libstereo_b200.so on
+torch's current stream; nothing here computes on the host and nothing falls back.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib as _l
+from .lib import ConvDesc, ProposalCfg, check, ptr, stream_ptr
+
+# constants of lib/model/utils/config.py that the hot path reads
+CFG = dict(
+    ANCHOR_RATIOS=[0.5, 1, 2], FPN_ANCHOR_SCALES=[32, 64, 128, 256, 512],
+    FPN_FEAT_STRIDES=[4, 8, 16, 32, 64],
+    TEST=dict(RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300, RPN_NMS_THRESH=0.7, NMS=0.3),
+    TRAIN=dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000, RPN_NMS_THRESH=0.7),
+    POOLING_SIZE=7, KPTS_GRID=28,
+)
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="default"):
+    """grow-only byte workspace per (device, tag); avoids cudaMalloc in steady state"""
+    key = (str(device), tag)
+    w = _ws_cache.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = w
+    return w
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------ NMS ----
+def nms_into(keep, dets, num_out, thresh):
+    """caller-allocated outputs, as nms.nms_cuda(keep, dets, num_out, thresh) (nms_gpu.py:8-10)"""
+    L = _l.load()
+    n = dets.shape[0]
+    assert dets.dim() == 2 and dets.shape[1] == 5 and keep.dtype == torch.int32 and num_out.dtype == torch.int32
+    dets = _f32c(dets)
+    nb = L.sb_nms_workspace_bytes(n)
+    ws = workspace(nb, dets.device, "nms")
+    check(L.sb_nms(ptr(dets), n, float(thresh), ptr(keep), ptr(num_out), ptr(ws), nb, stream_ptr()), "sb_nms")
+    return 1
+
+
+def nms(dets, thresh):
+    """-> int32 [K,1] indices kept (ascending), like nms_gpu (lib/model/nms/nms_gpu.py:7-12)"""
+    n = dets.shape[0]
+    keep = torch.zeros(n, 1, dtype=torch.int32, device=dets.device)
+    num_out = torch.zeros(1, dtype=torch.int32, device=dets.device)
+    if n == 0:
+        return keep
+    nms_into(keep, dets, num_out, thresh)
+    return keep[:int(num_out[0])]
+
+
+def nms_mask(dets, thresh):
+    L = _l.load()
+    n = dets.shape[0]
+    cb = (n + 63) // 64
+    mask = torch.zeros(n, cb, dtype=torch.int64, device=dets.device)
+    check(L.sb_nms_mask(ptr(_f32c(dets)), n, float(thresh), ptr(mask), stream_ptr()), "sb_nms_mask")
+    return mask
+
+
+# -------------------------------------------------------------- RoIAlign ----
+def roi_align_forward(ah, aw, scale, features, rois, output):
+    """roi_align.roi_align_forward_cuda(ah, aw, scale, features, rois, output) (functions/roi_align.py:24-27)"""
+    L = _l.load()
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        return 0                                   # roi_align_cuda.c:19-22
+    N, C, H, W = features.shape
+    check(L.sb_roi_align_forward(ptr(_f32c(features)), N, C, H, W, ptr(_f32c(rois)), rois.shape[0],
+                                 int(ah), int(aw), float(scale), ptr(output), stream_ptr()), "sb_roi_align_forward")
+    return 1
+
+
+def roi_align_backward(ah, aw, scale, top_grad, rois, bottom_grad):
+    L = _l.load()
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        return 0
+    N, C, H, W = bottom_grad.shape
+    check(L.sb_roi_align_backward(ptr(_f32c(top_grad)), N, C, H, W, ptr(_f32c(rois)), rois.shape[0],
+                                  int(ah), int(aw), float(scale), ptr(bottom_grad), stream_ptr()),
+          "sb_roi_align_backward")
+    return 1
+
+
+def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0):
+    """feats: 4 NHWC tensors (P2..P5); rois [R,5]; -> out [R,pooled,pooled,out_ld] NHWC"""
+    L = _l.load()
+    C = feats[0].shape[3]
+    R = rois.shape[0]
+    if out is None:
+        out = torch.empty(R, pooled, pooled, C, dtype=torch.float32, device=rois.device)
+    fp = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats])
+    hs = (ctypes.c_int * 4)(*[f.shape[1] for f in feats])
+    ws_ = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
+    check(L.sb_roi_align_pyramid_nhwc(fp, hs, ws_, C, float(im_h), ptr(_f32c(rois)), R, pooled, ptr(out),
+                                      out.shape[3], out_coff, stream_ptr()), "sb_roi_align_pyramid_nhwc")
+    return out
+
+
+# -------------------------------------------------------- proposal layer ----
+def make_proposal_cfg(cfg_key, feat_shapes, ratios=None, scales=None, strides=None, cfg=None):
+    cfg = CFG if cfg is None else cfg
+    pc = ProposalCfg()
+    ratios = cfg["ANCHOR_RATIOS"] if ratios is None else ratios
+    scales = cfg["FPN_ANCHOR_SCALES"] if scales is None else scales
+    strides = cfg["FPN_FEAT_STRIDES"] if strides is None else strides
+    pc.n_levels = len(feat_shapes)
+    for i, (h, w) in enumerate(feat_shapes):
+        pc.shapes[i][0], pc.shapes[i][1] = int(h), int(w)
+        pc.anchor_scales[i], pc.feat_strides[i] = int(scales[i]), int(strides[i])
+    pc.n_ratios = len(ratios)
+    for i, r in enumerate(ratios):
+        pc.ratios[i] = float(r)
+    pc.pre_nms_top_n = int(cfg[cfg_key]["RPN_PRE_NMS_TOP_N"])
+    pc.post_nms_top_n = int(cfg[cfg_key]["RPN_POST_NMS_TOP_N"])
+    pc.nms_thresh = float(cfg[cfg_key]["RPN_NMS_THRESH"])
+    return pc
+
+
+def proposal_layer(cls_prob, bbox_pred_lr, im_info, cfg_key, feat_shapes, pc=None):
+    """_ProposalLayer.forward (proposal_layer.py:42-145) -> rois_left, rois_right [B,N,5]"""
+    L = _l.load()
+    B, A = cls_prob.shape[:2]
+    pc = make_proposal_cfg(cfg_key, feat_shapes) if pc is None else pc
+    post = pc.post_nms_top_n
+    dev = cls_prob.device
+    rl = torch.empty(B, post, 5, dtype=torch.float32, device=dev)
+    rr = torch.empty(B, post, 5, dtype=torch.float32, device=dev)
+    nb = L.sb_proposal_workspace_bytes(B, A, pc.pre_nms_top_n)
+    ws = workspace(nb, dev, "proposal")
+    check(L.sb_proposal_layer(ptr(_f32c(cls_prob)), ptr(_f32c(bbox_pred_lr)), ptr(_f32c(im_info)), B, A,
+                              ctypes.byref(pc), ptr(rl), ptr(rr), ptr(ws), nb, stream_ptr()), "sb_proposal_layer")
+    return rl, rr
+
+
+def rpn_head_epilogue(head, B, P):
+    """raw fused head output [B*P, ld] -> cls_prob [B, 3P, 2], bbox_pred [B, 3P, 6]"""
+    L = _l.load()
+    dev = head.device
+    cls_prob = torch.empty(B, 3 * P, 2, dtype=torch.float32, device=dev)
+    bbox = torch.empty(B, 3 * P, 6, dtype=torch.float32, device=dev)
+    check(L.sb_rpn_head_epilogue(ptr(head), B, P, head.shape[-1], ptr(cls_prob), ptr(bbox), stream_ptr()),
+          "sb_rpn_head_epilogue")
+    return cls_prob, bbox
+
+
+# ----------------------------------------------------------- dense_align ----
+def calib_vec(p2, p3):
+    p2, p3 = np.asarray(p2, np.float64), np.asarray(p3, np.float64)
+    return np.array([p2[0, 0], p2[0, 2], p2[1, 2], p2[0, 3] - p3[0, 3]], np.float64)
+
+
+def dense_align(calib4, scale, im_left, im_right, box_left, keypoints, poses):
+    """align_parallel (dense_align.py:240-300) -> solve_status [D], best_dis [D]"""
+    L = _l.load()
+    iml = _f32c(im_left).reshape(3, *im_left.shape[-2:])
+    imr = _f32c(im_right).reshape(3, *im_right.shape[-2:])
+    H, W = iml.shape[1:]
+    D = box_left.shape[0]
+    dev = iml.device
+    status = torch.zeros(D, dtype=torch.float32, device=dev)
+    best = torch.zeros(D, dtype=torch.float32, device=dev)
+    if D == 0:
+        return status, best
+    nb = L.sb_dense_align_workspace_bytes(H, W, D)
+    ws = workspace(nb, dev, "dense_align")
+    c4 = (ctypes.c_double * 4)(*[float(v) for v in calib4])
+    check(L.sb_dense_align(ptr(iml), ptr(imr), H, W, c4, float(scale), ptr(_f32c(box_left)),
+                           ptr(_f32c(keypoints)), ptr(_f32c(poses)), D, ptr(status), ptr(best), ptr(ws), nb,
+                           stream_ptr()), "sb_dense_align")
+    return status, best
+
+
+# ------------------------------------------------------------- layer ops ----
+def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, shift=None, residual=None,
+              up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None):
+    """x: NHWC [N,H,W,in_ld]; wgt packed [Cout,kh,kw,Cin]; out: any tensor addressed through out_strides
+    = (n, h, w) strides in floats (default: dense NHWC of out.shape[-1] channels)."""
+    d = ConvDesc()
+    N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    d.in_, d.wgt, d.out = x.data_ptr(), wgt.data_ptr(), out.data_ptr()
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.up_src = up_src.data_ptr() if up_src is not None else None
+    d.N, d.H, d.W, d.Cin, d.Cout, d.kh, d.kw = N, H, W, Cin, Cout, kh, kw
+    d.stride, d.pad, d.Ho, d.Wo = stride, pad, Ho, Wo
+    d.in_ld = x.shape[3] if in_ld is None else in_ld
+    d.res_ld = residual.shape[-1] if residual is not None else 0
+    d.UH, d.UW = (up_src.shape[1], up_src.shape[2]) if up_src is not None else (0, 0)
+    d.relu = 1 if relu else 0
+    d.out_coff = out_coff
+    if out_strides is None:
+        ld = out.shape[-1]
+        out_strides = (Ho * Wo * ld, Wo * ld, ld)
+    d.out_n_stride, d.out_h_stride, d.out_w_stride = [int(s) for s in out_strides]
+    return d
+
+
+def conv2d(desc, impl="auto"):
+    L = _l.load()
+    if impl == "auto":
+        impl = "tc" if L.sb_conv2d_tc_supported(ctypes.byref(desc)) else "simt"
+    if impl == "tc":
+        check(L.sb_conv2d_tc(ctypes.byref(desc), stream_ptr()), "sb_conv2d_tc")
+    else:
+        check(L.sb_conv2d_simt(ctypes.byref(desc), stream_ptr()), "sb_conv2d_simt")
+    return impl
+
+
+def stem_conv(im_nchw, wgt, scale, shift):
+    L = _l.load()
+    N, _, H, W = im_nchw.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=im_nchw.device)
+    check(L.sb_stem_conv(ptr(_f32c(im_nchw)), N, H, W, ptr(wgt), ptr(scale), ptr(shift), ptr(out), stream_ptr()),
+          "sb_stem_conv")
+    return out
+
+
+def maxpool3x3s2_ceil(x):
+    L = _l.load()
+    N, H, W, C = x.shape
+
+    def osz(v):
+        o = (v - 3 + 1) // 2 + 1
+        return o - 1 if (o - 1) * 2 >= v else o
+    out = torch.empty(N, osz(H), osz(W), C, dtype=torch.float32, device=x.device)
+    check(L.sb_maxpool3x3s2_ceil(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_maxpool3x3s2_ceil")
+    return out
+
+
+def subsample2(x):
+    L = _l.load()
+    N, H, W, C = x.shape
+    out = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=torch.float32, device=x.device)
+    check(L.sb_subsample2(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_subsample2")
+    return out
+
+
+def kpts_tail(x, w, b, want_pred_all=False):
+    L = _l.load()
+    R, G, _, C = x.shape
+    dev = x.device
+    kp = torch.empty(R, 4 * G, dtype=torch.float32, device=dev)
+    lp = torch.empty(R, G, dtype=torch.float32, device=dev)
+    rp = torch.empty(R, G, dtype=torch.float32, device=dev)
+    ka = torch.empty(R, 6, G, dtype=torch.float32, device=dev) if want_pred_all else None
+    check(L.sb_kpts_tail(ptr(x), R, G, C, ptr(w), ptr(b), ptr(kp), ptr(lp), ptr(rp), ptr(ka), stream_ptr()),
+          "sb_kpts_tail")
+    return kp, lp, rp, ka
+
+
+def box_tail(fc7, w_cls, b_cls, w_box, b_box, w_dim, b_dim, n_classes):
+    L = _l.load()
+    R, K = fc7.shape
+    dev = fc7.device
+    cls_prob = torch.empty(R, n_classes, dtype=torch.float32, device=dev)
+    bbox = torch.empty(R, 6 * n_classes, dtype=torch.float32, device=dev)
+    dim = torch.empty(R, 5 * n_classes, dtype=torch.float32, device=dev)
+    check(L.sb_box_tail(ptr(fc7), R, K, n_classes, ptr(w_cls), ptr(b_cls), ptr(w_box), ptr(b_box), ptr(w_dim),
+                        ptr(b_dim), ptr(cls_prob), ptr(bbox), ptr(dim), stream_ptr()), "sb_box_tail")
+    return cls_prob, bbox, dim
+
+
+def test_decode(rois_left, rois_right, bbox_pred, dim_orien, kpts_prob, left_prob, right_prob, im_info,
+                n_classes=2, grid=28):
+    """test_net.py:138-212 -> pred_boxes_left [R,4nc], pred_boxes_right, dim_orien [R,5nc], pred_kpts [R,5]"""
+    L = _l.load()
+    R = rois_left.shape[0]
+    dev = rois_left.device
+    pbl = torch.empty(R, 4 * n_classes, dtype=torch.float32, device=dev)
+    pbr = torch.empty(R, 4 * n_classes, dtype=torch.float32, device=dev)
+    do = torch.empty(R, 5 * n_classes, dtype=torch.float32, device=dev)
+    pk = torch.empty(R, 5, dtype=torch.float32, device=dev)
+    check(L.sb_test_decode(ptr(_f32c(rois_left)), ptr(_f32c(rois_right)), ptr(_f32c(bbox_pred)),
+                           ptr(_f32c(dim_orien)), ptr(_f32c(kpts_prob)), ptr(_f32c(left_prob)),
+                           ptr(_f32c(right_prob)), ptr(_f32c(im_info)), R, n_classes, grid, ptr(pbl), ptr(pbr),
+                           ptr(do), ptr(pk), stream_ptr()), "sb_test_decode")
+    return pbl, pbr, do, pk
+
+
+def l2_flush(buf):
+    L = _l.load()
+    check(L.sb_fill(ptr(buf), buf.numel(), 0.0, stream_ptr()), "sb_fill")
+
+
+def launch_count():
+    return int(_l.load().sb_launch_count())

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI shared library builds, loads without a GPU and exports every symbol that
+include/stereo_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    from stereo_rcnn_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "stereo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(so_path):
+    lib = ctypes.CDLL(so_path)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "declared in include/stereo_b200.h but not exported: " + n
+
+
+def test_python_binding_matches_header(so_path):
+    from stereo_rcnn_b200 import lib as L
+    assert sorted(L.EXPORTS) == declared_symbols()
+    lib = L.load()
+    assert lib.sb_version() == 100
+    assert lib.sb_nms_workspace_bytes(6000) >= 6000 * 94 * 8
+    assert lib.sb_proposal_workspace_bytes(1, 298476, 6000) > 2 * 6000 * 94 * 8
+    assert lib.sb_dense_align_workspace_bytes(600, 1987, 4) >= 2 * 16 * 1200 * 3974
+
+
+def test_struct_layout_matches_c(so_path):
+    """sizeof of the ctypes mirrors equals what the header implies (catches field drift)"""
+    from stereo_rcnn_b200.lib import ConvDesc, ProposalCfg
+    assert ctypes.sizeof(ConvDesc) == 7 * 8 + 17 * 4 + 4 + 3 * 8          # 7 ptrs, 17 ints (+pad), 3 long long
+    assert ctypes.sizeof(ProposalCfg) == 4 + 64 + 32 + 32 + 4 + 32 + 4 + 4 + 4 + 4  # incl. 8-byte alignment pads
+
+
+def test_no_oracle_import_in_product():
+    """the product package must never import the oracle (parity would be void)"""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "stereo_rcnn_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,198 @@
+"""GPU parity tests of the dense layer kernels and of the composed forward against the CPU
+oracle (which is pinned to the reference's own forward graph, tests/golden/forward_small.npz).
+Tolerance for FP32 tensors: 1e-3 relative (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as OM
+from oracle import ops as O
+from stereo_rcnn_b200 import engine as E
+from stereo_rcnn_b200 import ops as G
+from stereo_rcnn_b200.synth import synth_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    return a.contiguous().cuda()
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def run_conv(x, w, impl, stride=1, pad=0, scale=None, shift=None, residual=None, up_src=None, relu=False):
+    """x NCHW cpu, w [Co,Ci,kh,kw] cpu -> NCHW cpu result through the C ABI"""
+    Co, Ci, kh, kw = w.shape
+    xg = cu(nhwc(x))
+    N, H, W = xg.shape[:3]
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    out = torch.empty(N, Ho, Wo, Co, device="cuda")
+    d = G.conv_desc(xg, cu(w.permute(0, 2, 3, 1)), out, Ci, Co, kh, kw, stride, pad, Ho, Wo,
+                    scale=None if scale is None else cu(scale), shift=None if shift is None else cu(shift),
+                    residual=None if residual is None else cu(nhwc(residual)),
+                    up_src=None if up_src is None else cu(nhwc(up_src)), relu=relu)
+    used = G.conv2d(d, impl)
+    assert used == impl
+    torch.cuda.synchronize()
+    return out.permute(0, 3, 1, 2).cpu()
+
+
+def ref_conv(x, w, stride=1, pad=0, scale=None, shift=None, residual=None, up_src=None, relu=False):
+    y = F.conv2d(x.double(), w.double(), stride=stride, padding=pad)
+    if scale is not None:
+        y = y * scale.double().view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.double().view(1, -1, 1, 1)
+    if residual is not None:
+        y = y + residual.double()
+    if up_src is not None:
+        y = y + F.interpolate(up_src.double(), size=y.shape[2:], mode="bilinear", align_corners=True)
+    return (F.relu(y) if relu else y).float()
+
+
+CONV_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad
+    (2, 64, 19, 33, 64, 1, 1, 0),
+    (1, 64, 20, 31, 256, 3, 1, 1),
+    (2, 128, 9, 17, 48, 3, 1, 1),
+    (1, 256, 14, 14, 256, 3, 1, 1),
+    (3, 1024, 5, 7, 32, 1, 1, 0),
+    (1, 64, 21, 23, 128, 1, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(case):
+    N, Ci, H, W, Co, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+    y = run_conv(x, w, "simt", s, p, sc, sh, relu=True)
+    assert rel_err(y, ref_conv(x, w, s, p, sc, sh, relu=True)) < 1e-5
+    Ho, Wo = y.shape[2:]
+    res = torch.randn(N, Co, Ho, Wo, generator=g)
+    up = torch.randn(N, Co, (Ho + 1) // 2, (Wo + 1) // 2, generator=g)
+    y = run_conv(x, w, "simt", s, p, None, sh, residual=res, up_src=up)
+    assert rel_err(y, ref_conv(x, w, s, p, None, sh, residual=res, up_src=up)) < 1e-5
+
+
+def test_stem_maxpool_subsample():
+    sd = OM.make_state_dict(3)
+    g = torch.Generator().manual_seed(0)
+    im = torch.randn(2, 3, 67, 101, generator=g) * 50
+    eng_w = sd["RCNN_layer0.0.weight"].permute(0, 2, 3, 1).contiguous()
+    s = sd["RCNN_layer0.1.weight"] / torch.sqrt(sd["RCNN_layer0.1.running_var"] + 1e-5)
+    b = sd["RCNN_layer0.1.bias"] - sd["RCNN_layer0.1.running_mean"] * s
+    y = G.stem_conv(cu(im), cu(eng_w), cu(s), cu(b))
+    ref = F.relu(OM._bn(OM._conv(im, sd, "RCNN_layer0.0", stride=2, pad=3), sd, "RCNN_layer0.1"))
+    assert rel_err(y.permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+    mp = G.maxpool3x3s2_ceil(y)
+    refp = F.max_pool2d(y.permute(0, 3, 1, 2).cpu(), 3, 2, 0, ceil_mode=True)
+    assert mp.shape[1:3] == refp.shape[2:]
+    np.testing.assert_array_equal(mp.permute(0, 3, 1, 2).cpu().numpy(), refp.numpy())
+    ss = G.subsample2(mp)
+    np.testing.assert_array_equal(ss.cpu().numpy(), mp[:, ::2, ::2].cpu().numpy())
+
+
+def test_head_tails_and_decode():
+    sd = OM.make_state_dict(3)
+    g = torch.Generator().manual_seed(1)
+    R = 37
+    fc7 = torch.randn(R, 2048, generator=g).abs()
+    cls, bbox, dim = G.box_tail(cu(fc7), cu(sd["RCNN_cls_score.weight"]), cu(sd["RCNN_cls_score.bias"]),
+                                cu(sd["RCNN_bbox_pred.weight"]), cu(sd["RCNN_bbox_pred.bias"]),
+                                cu(sd["RCNN_dim_orien_pred.weight"]), cu(sd["RCNN_dim_orien_pred.bias"]), 2)
+    assert rel_err(bbox.cpu(), F.linear(fc7, sd["RCNN_bbox_pred.weight"], sd["RCNN_bbox_pred.bias"])) < 1e-5
+    assert rel_err(dim.cpu(), F.linear(fc7, sd["RCNN_dim_orien_pred.weight"], sd["RCNN_dim_orien_pred.bias"])) < 1e-5
+    assert rel_err(cls.cpu(), F.softmax(F.linear(fc7, sd["RCNN_cls_score.weight"], sd["RCNN_cls_score.bias"]), 1)) < 1e-5
+    x = torch.randn(R, 256, 28, 28, generator=g).abs()
+    kp, lb, rb, ka = G.kpts_tail(cu(nhwc(x)), cu(sd["kpts_class.weight"].reshape(6, 256)), cu(sd["kpts_class.bias"]),
+                                 want_pred_all=True)
+    ka_ref = OM._conv(x, sd, "kpts_class").sum(2)
+    assert rel_err(ka.cpu(), ka_ref) < 1e-4
+    assert rel_err(kp.cpu(), F.softmax(ka_ref[:, :4].reshape(R, -1), 1)) < 1e-3
+    assert rel_err(lb.cpu(), F.softmax(ka_ref[:, 4], 1)) < 1e-3
+    assert rel_err(rb.cpu(), F.softmax(ka_ref[:, 5], 1)) < 1e-3
+    # test-time decode on the oracle's own probabilities: exact argmax / decode chain
+    rs = np.random.RandomState(3)
+    x1 = rs.rand(R) * 1000; y1 = rs.rand(R) * 300
+    rl = np.stack([np.zeros(R), x1, y1, x1 + rs.rand(R) * 300 + 5, y1 + rs.rand(R) * 200 + 5], 1).astype(np.float32)
+    rr = rl.copy(); rr[:, 1] -= 20; rr[:, 3] -= 20
+    info = np.array([600, 1987, 1.6], np.float32)
+    bp = (rs.randn(R, 12) * 0.8).astype(np.float32)
+    dp = rs.randn(R, 10).astype(np.float32)
+    kpn, lbn, rbn = kp.cpu().numpy(), lb.cpu().numpy(), rb.cpu().numpy()
+    ref = O.test_decode(rl, rr, cls.cpu().numpy(), bp, dp, kpn, lbn, rbn, info)
+    out = G.test_decode(cu(rl), cu(rr), cu(bp), cu(dp), cu(kpn), cu(lbn), cu(rbn), cu(info))
+    for a, b in zip(out, ref[1:]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+
+
+def test_forward_small_vs_oracle_and_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_small.npz"))
+    H, W = int(g["H"]), int(g["W"])
+    left, right = synth_pair(H, W, int(g["seed"]), int(g["shift"]))
+    sd = OM.make_state_dict(int(g["weight_seed"]))
+    iml, imr = torch.from_numpy(left)[None], torch.from_numpy(right)[None]
+    info = torch.tensor([[float(H), float(W), 1.0]])
+    o = OM.forward(sd, iml, imr, info)                                  # CPU oracle, every stage
+    eng = E.StereoRCNNEngine(sd, "cuda", conv_impl=os.environ.get("SB_CONV_IMPL", "auto"))
+    r = eng.forward(iml.cuda(), imr.cuda(), info.cuda(), keep_features=True)
+    torch.cuda.synchronize()
+    # stage 1: trunk + FPN (left image = batch 0, right = batch 1)
+    for k in ("c2", "c3", "c4", "c5", "p5", "p4", "p3", "p2", "p6"):
+        got = r["feats"][k].permute(0, 3, 1, 2).cpu().numpy()
+        assert rel_err(got[0:1], o["left"][k].numpy()) < 1e-3, k
+        assert rel_err(got[1:2], o["right"][k].numpy()) < 1e-3, k
+    # stage 2: RPN head
+    assert rel_err(r["rpn_cls_prob"].cpu().numpy(), o["rpn_cls_prob"].numpy()) < 1e-3
+    assert rel_err(r["rpn_bbox_pred"].cpu().numpy(), o["rpn_bbox_pred"].numpy()) < 1e-3
+    # stage 3: proposal layer on the *oracle's* RPN tensors -> bit-exact indices / boxes
+    rl, rr = G.proposal_layer(o["rpn_cls_prob"].cuda(), o["rpn_bbox_pred"].cuda(), info.cuda(), "TEST", o["rpn_shapes"])
+    np.testing.assert_array_equal(rl.cpu().numpy(), o["rois_left"].numpy())
+    np.testing.assert_array_equal(rr.cpu().numpy(), o["rois_right"].numpy())
+    # stage 4: heads on the oracle's rois (identical inputs) within 1e-3
+    h = eng.heads(r["feats"], 1, rl.view(-1, 5), rr.view(-1, 5), float(H))
+    torch.cuda.synchronize()
+    assert rel_err(h["pooled_box"].permute(0, 3, 1, 2).cpu().numpy(), o["pooled_box"].numpy()) < 1e-3
+    assert rel_err(h["pooled_kpts"].permute(0, 3, 1, 2).cpu().numpy(), o["pooled_kpts"].numpy()) < 1e-3
+    for k in ("fc7", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_pred_all", "kpts_prob", "left_border_prob",
+              "right_border_prob"):
+        assert rel_err(h[k].cpu().numpy().reshape(o[k].shape), o[k].numpy()) < 1e-3, k
+    # the reference's own forward outputs (golden): same heads within tolerance
+    for k in ("cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob"):
+        assert rel_err(h[k].cpu().numpy().reshape(g[k].shape), g[k]) < 1e-3, k
+    # end to end (GPU proposals from GPU RPN): most proposals coincide with the oracle's
+    a = {tuple(np.round(x, 1)) for x in r["rois_left"][0].cpu().numpy()}
+    b = {tuple(np.round(x, 1)) for x in o["rois_left"][0].numpy()}
+    assert len(a & b) >= 0.9 * len(b)
+
+
+def test_reference_module_interface(golden_dir):
+    from stereo_rcnn_b200.model.stereo_rcnn.resnet import resnet
+    sd = OM.make_state_dict(3)
+    m = resnet(("__background__", "Car"), 101, pretrained=False)
+    m.create_architecture()
+    m.load_state_dict(sd, strict=False)
+    m.cuda().eval()
+    left, right = synth_pair(96, 160, 1, 5)
+    d = torch.zeros(1).cuda()
+    out = m(cu(left)[None], cu(right)[None], torch.tensor([[96., 160., 1.0]]).cuda(), d, d, d, d, d, d)
+    assert len(out) == 15
+    assert out[0].shape == (1, 300, 5) and out[2].shape == (1, 300, 2) and out[3].shape == (1, 300, 12)
+    assert out[4].shape == (1, 300, 10) and out[5].shape == (300, 112) and out[6].shape == (300, 28)
+    with pytest.raises(NotImplementedError):
+        m.train()
