@@ -29,106 +29,7 @@ STRIDES = [1, 2, 2, 2]
 N_CLASSES = 2
 
 
-# --------------------------------------------------------------------------
-# state dict layout
-# --------------------------------------------------------------------------
-def param_shapes(n_classes=N_CLASSES):
-    """ordered {key: shape} of every tensor the forward reads (reference key names)"""
-    s = OrderedDict()
-
-    def conv(k, co, ci, kh, kw, bias):
-        s[k + ".weight"] = (co, ci, kh, kw)
-        if bias:
-            s[k + ".bias"] = (co,)
-
-    def bn(k, c):
-        for n in ("weight", "bias", "running_mean", "running_var"):
-            s[k + "." + n] = (c,)
-
-    conv("RCNN_layer0.0", 64, 3, 7, 7, False)
-    bn("RCNN_layer0.1", 64)
-    inpl = 64
-    for li, (nb, pl) in enumerate(zip(LAYERS, PLANES)):
-        for b in range(nb):
-            p = "RCNN_layer%d.0.%d" % (li + 1, b)
-            conv(p + ".conv1", pl, inpl, 1, 1, False); bn(p + ".bn1", pl)
-            conv(p + ".conv2", pl, pl, 3, 3, False); bn(p + ".bn2", pl)
-            conv(p + ".conv3", pl * 4, pl, 1, 1, False); bn(p + ".bn3", pl * 4)
-            if b == 0:
-                conv(p + ".downsample.0", pl * 4, inpl, 1, 1, False); bn(p + ".downsample.1", pl * 4)
-            inpl = pl * 4
-    conv("RCNN_toplayer", 256, 2048, 1, 1, True)
-    for i in (1, 2, 3):
-        conv("RCNN_smooth%d" % i, 256, 256, 3, 3, True)
-    conv("RCNN_latlayer1", 256, 1024, 1, 1, True)
-    conv("RCNN_latlayer2", 256, 512, 1, 1, True)
-    conv("RCNN_latlayer3", 256, 256, 1, 1, True)
-    conv("RCNN_rpn.RPN_Conv", 512, 256, 3, 3, True)
-    conv("RCNN_rpn.RPN_cls_score", 6, 1024, 1, 1, True)
-    conv("RCNN_rpn.RPN_bbox_pred_left_right", 18, 1024, 1, 1, True)
-    conv("RCNN_top.0", 2048, 512, 7, 7, True)
-    conv("RCNN_top.3", 2048, 2048, 1, 1, True)
-    for i in range(0, 12, 2):
-        conv("RCNN_kpts.%d" % i, 256, 256, 3, 3, True)
-    s["RCNN_kpts.12.weight"] = (256, 256, 2, 2)      # ConvTranspose2d: (Cin, Cout, kh, kw)
-    s["RCNN_kpts.12.bias"] = (256,)
-    s["RCNN_cls_score.weight"] = (n_classes, 2048); s["RCNN_cls_score.bias"] = (n_classes,)
-    s["RCNN_bbox_pred.weight"] = (6 * n_classes, 2048); s["RCNN_bbox_pred.bias"] = (6 * n_classes,)
-    s["RCNN_dim_orien_pred.weight"] = (5 * n_classes, 2048); s["RCNN_dim_orien_pred.bias"] = (5 * n_classes,)
-    conv("kpts_class", 6, 256, 1, 1, True)
-    return s
-
-
-def make_state_dict(seed=3, n_classes=N_CLASSES, head_gain=1.0):
-    """Deterministic synthetic weights, one private RNG stream per key.
-
-    "Variance-preserving" variant of the reference's random init (SURVEY 7,
-    hard part "random-init weights saturate the RPN"): He-normal conv weights,
-    non-trivial frozen-BN statistics, and a small ``bn3.weight`` so the residual
-    trunk neither explodes nor collapses; head weights scaled so that RPN scores
-    and box deltas are spread out (non-degenerate NMS / top-k work).
-    """
-    sd = OrderedDict()
-    for k, shp in param_shapes(n_classes).items():
-        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
-        leaf = k.rsplit(".", 1)[1]
-        is_bn = ".bn" in k or "downsample.1" in k or k.startswith("RCNN_layer0.1")
-        if is_bn:
-            n = shp[0]
-            if leaf == "weight":
-                lo, hi = (0.15, 0.35) if ".bn3." in k else (0.8, 1.2)
-                t = torch.rand(n, generator=g) * (hi - lo) + lo
-            elif leaf == "bias":
-                t = torch.randn(n, generator=g) * 0.05
-            elif leaf == "running_mean":
-                t = torch.randn(n, generator=g) * 0.1
-            else:
-                t = torch.rand(n, generator=g) * 0.4 + 0.8
-        elif leaf == "bias":
-            t = torch.randn(shp, generator=g) * 0.02
-        else:
-            fan_in = int(np.prod(shp[1:]))
-            if k.startswith("RCNN_kpts.12"):
-                fan_in = shp[0]
-            std = (2.0 / fan_in) ** 0.5
-            if k.startswith(("RCNN_cls_score", "RCNN_bbox_pred", "RCNN_dim_orien_pred",
-                             "RCNN_rpn.RPN_cls_score", "RCNN_rpn.RPN_bbox_pred", "kpts_class")):
-                std = head_gain * (1.0 / fan_in) ** 0.5
-            if k.startswith("RCNN_rpn.RPN_bbox_pred"):
-                std *= 0.25
-            # fixed gains (calibrated once on a 200x333 input so that every stage's
-            # activations have rms ~1; see DESIGN.md "synthetic weights")
-            for pre, gain in _GAINS:
-                if k.startswith(pre):
-                    std *= gain
-            t = torch.randn(shp, generator=g) * std
-        sd[k] = t.float().contiguous()
-    return sd
-
-
-_GAINS = (("RCNN_layer0.0", 1.0 / 64), ("RCNN_toplayer", 0.0625), ("RCNN_latlayer1", 0.075),
-          ("RCNN_latlayer2", 0.22), ("RCNN_latlayer3", 0.32), ("RCNN_smooth", 0.5),
-          ("RCNN_rpn.RPN_cls_score", 2.0), ("kpts_class", 0.1))
+from stereo_rcnn_b200.synth import make_state_dict, param_shapes  # noqa: E402,F401  (shared synthetic weights)
 
 
 # --------------------------------------------------------------------------

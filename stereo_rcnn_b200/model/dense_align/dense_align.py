@@ -1,6 +1,6 @@
 """``align_parallel`` with the reference's signature (lib/model/dense_align/dense_align.py:240-300):
 one C-ABI call (two kernel launches) instead of the per-RoI Python loop + grid_sample passes."""
-from ... import ops as _ops
+from stereo_rcnn_b200 import ops as _ops
 
 
 def align_parallel(calib, scale, im_left, im_right, box_left, keypoints, poses):

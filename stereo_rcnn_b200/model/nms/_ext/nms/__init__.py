@@ -1,6 +1,6 @@
 """``nms.nms_cuda`` -- same name and argument order as the reference's cffi symbol
 (lib/model/nms/src/nms_cuda.h:4-5, bound in lib/model/nms/_ext/nms/__init__.py)."""
-from .... import ops as _ops
+from stereo_rcnn_b200 import ops as _ops
 
 __all__ = ["nms_cuda"]
 

@@ -1,6 +1,6 @@
 """``roi_align.roi_align_forward_cuda`` / ``roi_align_backward_cuda`` -- names and argument order
 of lib/model/roi_align/src/roi_align_cuda.h:1-5."""
-from .... import ops as _ops
+from stereo_rcnn_b200 import ops as _ops
 
 __all__ = ["roi_align_forward_cuda", "roi_align_backward_cuda"]
 

@@ -2,7 +2,7 @@
 (lib/model/rpn/proposal_layer.py:26-145); the whole layer is one stream-ordered C-ABI call."""
 import torch.nn as nn
 
-from ... import ops as _ops
+from stereo_rcnn_b200 import ops as _ops
 from ..utils.config import cfg
 
 

@@ -12,7 +12,7 @@ import math
 import torch
 import torch.nn as nn
 
-from ... import engine as _engine
+from stereo_rcnn_b200 import engine as _engine
 from ..utils.config import cfg
 
 _LAYERS = [3, 4, 23, 3]

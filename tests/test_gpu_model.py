@@ -89,6 +89,60 @@ def test_conv_simt_fp32(case):
     assert rel_err(y, ref_conv(x, w, s, p, None, sh, residual=res, up_src=up)) < 1e-5
 
 
+TC_CASES = [
+    # N, Ci, H, W, Co, k
+    (2, 64, 19, 33, 64, 1),
+    (1, 64, 20, 31, 256, 3),
+    (2, 128, 9, 17, 48, 3),
+    (3, 256, 14, 14, 256, 3),
+    (3, 1024, 5, 7, 32, 1),
+    (1, 2048, 19, 63, 256, 1),
+    (1, 256, 38, 125, 512, 3),
+    (300, 25088, 1, 1, 2048, 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_tf32(case):
+    """tcgen05 kind::tf32 implicit GEMM vs fp64 reference: error of a TF32 product-sum, << 1e-3 rel"""
+    N, Ci, H, W, Co, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+    p = k // 2
+    y = run_conv(x, w, "tc", 1, p, sc, sh, relu=True)
+    assert rel_err(y, ref_conv(x, w, 1, p, sc, sh, relu=True)) < 1e-3
+    if N * H * W * Co < 4e6:
+        res = torch.randn(N, Co, H, W, generator=g)
+        up = torch.randn(N, Co, (H + 1) // 2, (W + 1) // 2, generator=g)
+        y = run_conv(x, w, "tc", 1, p, None, sh, residual=res, up_src=up)
+        assert rel_err(y, ref_conv(x, w, 1, p, None, sh, residual=res, up_src=up)) < 1e-3
+
+
+def test_conv_tc_strided_outputs():
+    """channel-offset (RPN L/R concat) and scattered (2x2 deconv) stores"""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 6, 10, generator=g)
+    w = torch.randn(96, 64, 1, 1, generator=g) / 8
+    xg = cu(nhwc(x))
+    cat = torch.zeros(2, 6, 10, 256, device="cuda")
+    d = G.conv_desc(xg, cu(w.permute(0, 2, 3, 1)), cat, 64, 96, 1, 1, 1, 0, 6, 10, out_coff=128,
+                    out_strides=(6 * 10 * 256, 10 * 256, 256))
+    assert G.conv2d(d, "tc") == "tc"
+    ref = ref_conv(x, w)
+    got = cat.cpu()
+    assert rel_err(got[..., 128:224].permute(0, 3, 1, 2), ref) < 1e-3
+    assert got[..., :128].abs().max() == 0 and got[..., 224:].abs().max() == 0
+    up = torch.zeros(2, 12, 20, 96, device="cuda")
+    d = G.conv_desc(xg, cu(w.permute(0, 2, 3, 1)), up[:, 1:, 1:], 64, 96, 1, 1, 1, 0, 6, 10,
+                    out_strides=(12 * 20 * 96, 2 * 20 * 96, 2 * 96))
+    G.conv2d(d, "tc")
+    got = up.cpu()
+    assert rel_err(got[:, 1::2, 1::2].permute(0, 3, 1, 2), ref) < 1e-3
+    assert got[:, 0::2].abs().max() == 0 and got[:, :, 0::2].abs().max() == 0
+
+
 def test_stem_maxpool_subsample():
     sd = OM.make_state_dict(3)
     g = torch.Generator().manual_seed(0)
