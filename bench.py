@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/sec of the Stereo R-CNN hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU port of the reference path
+
+Workload (config[1] of BASELINE.json): batch-1 inference, one synthetic KITTI-shape stereo pair
+per GPU per step (1242x375 resized by 1.6 -> 2 x [1,3,600,1987] fp32), full pipeline:
+trunk+FPN (L and R), stereo RPN, proposal layer, RoIAlign, box + keypoint heads, test-time decode,
+per-class NMS, and dense_align on D=32 synthetic poses (the scipy solver that produces poses in the
+reference is a CPU stage outside the kernels).  N>1: one process per GPU, one
+pair per rank per step (weak scaling), one NCCL all-gather of the fixed-size detection records.
+
+One JSON line on stdout (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+through the public forward with pinned-host inputs (H2D inside the timed region) and a D2H read of
+the detection record.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_NET, W_NET, SCALE = 600, 1987, 1.6
+D_ALIGN = 32
+N_ROIS = 300
+REC_COLS = 2 + 8 + 8 + 10 + 5        # scores, boxes L/R, dim_orien, kpts  (per RoI)
+
+# algorithmic MACs per *pair* at test (SURVEY 8 header / BASELINE.md 3), for the roofline line
+TC_GMACS_PER_PAIR = 2 * (15.88 + 22.64 + 123.58 + 17.89 + 66.99 + 117.37) + 2.45 + 16.7 + 223.9
+# the stem (2.81 GMAC/image) runs on the SIMT kernel and is excluded from the tensor-core FLOPs
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------
+def make_inputs(rank):
+    from stereo_rcnn_b200.synth import DEMO_P2, DEMO_P3, gen_rois, synth_pair
+    left, right = synth_pair(H_NET, W_NET, seed=3 + rank, shift=48)
+    b, k, p = gen_rois(D_ALIGN, seed=3 + rank)
+    return left, right, (b, k, p), (DEMO_P2, DEMO_P3)
+
+
+class Pipeline(object):
+    """the call a user makes: images in -> detection record + refined disparities out"""
+
+    def __init__(self, device):
+        from stereo_rcnn_b200 import engine, ops
+        from stereo_rcnn_b200.synth import make_state_dict
+        self.ops, self.dev = ops, device
+        self.eng = engine.StereoRCNNEngine(make_state_dict(3), device)
+        self.info = torch.tensor([[H_NET, W_NET, SCALE]], dtype=torch.float32, device=device)
+
+    def step(self, iml, imr, calib4, rois3d):
+        ops = self.ops
+        o = self.eng.forward(iml, imr, self.info)
+        pbl, pbr, dimo, pk = ops.test_decode(o["rois_left"][0], o["rois_right"][0], o["bbox_pred"][0],
+                                             o["dim_orien_pred"][0], o["kpts_prob"], o["left_border_prob"],
+                                             o["right_border_prob"], self.info[0])
+        keep, nkeep = ops.class_nms(o["cls_prob"][0], pbl, 1, 0.05, 0.3)
+        st, dis = ops.dense_align(calib4, SCALE32, iml, imr, *rois3d)
+        rec = torch.cat((o["cls_prob"][0], pbl, pbr, dimo, pk), 1)            # [300, 33] detection record
+        return rec, keep, nkeep, st, dis
+
+
+SCALE32 = float(np.float32(SCALE))
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from stereo_rcnn_b200 import ops
+    left, right, (b, k, p), (P2, P3) = make_inputs(rank)
+    calib4 = ops.calib_vec(P2, P3)
+    host_l = torch.from_numpy(left)[None].pin_memory()
+    host_r = torch.from_numpy(right)[None].pin_memory()
+    iml, imr = host_l.to(dev), host_r.to(dev)
+    rois3d = tuple(torch.from_numpy(x).to(dev) for x in (b, k, p))
+    pipe = Pipeline(dev)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+    gathered = torch.empty(world, N_ROIS, REC_COLS, device=dev) if world > 1 else None
+    host_rec = torch.empty(N_ROIS, REC_COLS).pin_memory()
+    host_dis = torch.empty(D_ALIGN).pin_memory()
+
+    def step_resident():
+        rec, keep, nkeep, st, dis = pipe.step(iml, imr, calib4, rois3d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)
+        return rec, dis
+
+    def step_e2e():
+        a = host_l.to(dev, non_blocking=True)
+        c = host_r.to(dev, non_blocking=True)
+        rec, keep, nkeep, st, dis = pipe.step(a, c, calib4, rois3d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)
+        host_rec.copy_(rec, non_blocking=True)
+        host_dis.copy_(dis, non_blocking=True)
+        return rec, dis
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            ops.l2_flush(flush)          # untimed, between iterations
+            s.record()
+            fn()
+            e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = sum(s.elapsed_time(e) for s, e in ev)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t[0])
+        return total_ms
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    total_ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    launches = (ops.launch_count() - l0) // (args.steps + max(args.warmup, 3))
+    e2e_ms = timed(step_e2e, args.steps, 1)
+    sampler.stop_flag = True
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms / 1e3)
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live with CUDA events ----
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        pk = peaks()
+        conv_ms = conv_time_per_step(pipe, iml, imr)
+        tflops = 2 * TC_GMACS_PER_PAIR * 1e9 / (conv_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM, all conv/FC launches of one step)",
+                "achieved": round(tflops, 2), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(tflops / pk["bf16_tflops_sustained"], 4), "traffic": None,
+                "peak_source": pk["src"] + " cuBLAS bf16 sustained (kind::tf32 issues at half that rate)",
+                "frac_of_tf32_rate": round(tflops / (pk["bf16_tflops_sustained"] / 2), 4),
+                "conv_ms_per_step": round(conv_ms, 3), "share_of_step": round(conv_ms / ms_per_step, 3)}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline_sample()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    out = {
+        "metric": "stereo pairs/sec (1242x375)", "value": round(value, 3), "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: batch-1 inference per GPU, synthetic KITTI-shape pair 2x[1,3,600,1987], "
+                               "full pipeline incl. dense_align (D=%d synthetic poses)" % D_ALIGN,
+                   "weights": "seeded variance-preserving random init (stereo_rcnn_b200.synth.make_state_dict(3))",
+                   "l2": "256 MB flush between timed iterations", "parallelism": "dp%d (1 pair/rank)" % world},
+        "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s",
+                "h2d_bytes_per_step": int(host_l.numel() * 4 * 2),
+                "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},
+        "gpu_launches": int(launches) * args.steps,
+        "clocks": sampler.summary(), "roofline": roof,
+    }
+    if cpu_base is not None:
+        out["cpu_baseline"] = cpu_base
+    print(json.dumps(out))
+
+
+def conv_time_per_step(pipe, iml, imr):
+    """sum of CUDA-event durations of every tcgen05 conv launch of one forward (same stream)"""
+    from stereo_rcnn_b200 import ops
+    eng = pipe.eng
+    events = []
+    orig = ops.conv2d
+
+    def timed_conv(desc, impl="auto"):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        used = orig(desc, impl)
+        e.record()
+        if used == "tc":
+            events.append((s, e))
+        return used
+    ops.conv2d = timed_conv
+    try:
+        best = None
+        for _ in range(3):
+            events.clear()
+            eng.forward(iml, imr, pipe.info)
+            torch.cuda.synchronize()
+            t = sum(s.elapsed_time(e) for s, e in events)
+            best = t if best is None else min(best, t)
+    finally:
+        ops.conv2d = orig
+    return best
+
+
+# ----------------------------------------------------------------------------------------------
+def _cpu_threads():
+    n = os.cpu_count() or 1
+    import torch.nn.functional as F
+    x, w = torch.randn(1, 64, 48, 64), torch.randn(64, 64, 3, 3)
+    best, best_t = 1, None
+    for nt in sorted({1, n}):
+        torch.set_num_threads(nt)
+        F.conv2d(x, w, padding=1)
+        t = time.time()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        t = time.time() - t
+        if best_t is None or t < best_t:
+            best, best_t = nt, t
+    torch.set_num_threads(best)
+    os.environ["OMP_NUM_THREADS"] = str(best)
+    return best
+
+
+def cpu_port_step(sd, left, right, crop_w, rois3d, calib):
+    """one pass of the hot path on the CPU port of the reference (oracle): forward + decode + NMS + dense_align
+    on a width-`crop_w` crop of the pair; returns seconds"""
+    from oracle import model as OM
+    from oracle import ops as O
+    iml = torch.from_numpy(left[:, :, :crop_w].copy())[None]
+    imr = torch.from_numpy(right[:, :, :crop_w].copy())[None]
+    info = torch.tensor([[float(H_NET), float(crop_w), SCALE]])
+    t = time.time()
+    o = OM.forward(sd, iml, imr, info)
+    dec = O.test_decode(o["rois_left"][0].numpy(), o["rois_right"][0].numpy(), o["cls_prob"].numpy(),
+                        o["bbox_pred"].numpy(), o["dim_orien_pred"].numpy(), o["kpts_prob"].numpy(),
+                        o["left_border_prob"].numpy(), o["right_border_prob"].numpy(), info[0].numpy())
+    O.per_class_nms(dec[0], dec[1], 1)
+    b, k, p = rois3d
+    O.dense_align(calib, SCALE32, left, right, b, k, p)
+    return time.time() - t
+
+
+def pick_crop(threads):
+    """bound one CPU step to ~<= 8 s: probe the conv rate, then pick the crop width"""
+    import torch.nn.functional as F
+    x, w = torch.randn(1, 256, 38, 125), torch.randn(256, 256, 3, 3)
+    F.conv2d(x, w, padding=1)
+    t = time.time()
+    for _ in range(3):
+        F.conv2d(x, w, padding=1)
+    rate = 3 * 2 * 38 * 125 * 256 * 256 * 9 / (time.time() - t)        # FLOP/s
+    full = 2 * (TC_GMACS_PER_PAIR + 5.6) * 1e9 / rate
+    for frac, wcrop in ((1.0, W_NET), (0.5, 993), (0.25, 497), (0.125, 248)):
+        if full * frac <= 8.0 or wcrop == 248:
+            return wcrop, frac
+
+
+def cpu_baseline_sample():
+    from oracle import ops as O
+    from stereo_rcnn_b200.synth import make_state_dict
+    threads = _cpu_threads()
+    left, right, rois3d, (P2, P3) = make_inputs(0)
+    wcrop, frac = pick_crop(threads)
+    sd = make_state_dict(3)
+    sec = cpu_port_step(sd, left, right, wcrop, rois3d, O.calib_vec(P2, P3))
+    return {"value": round((wcrop / W_NET) / sec, 5), "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "1 pass of the oracle (CPU port of the reference forward + decode + NMS + dense_align D=%d) on a "
+                      "600x%d crop of the pair (%.3f of the pixels), scaled to full pairs" % (D_ALIGN, wcrop, wcrop / W_NET)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import ops as O
+    from stereo_rcnn_b200.synth import make_state_dict
+    threads = _cpu_threads()
+    left, right, rois3d, (P2, P3) = make_inputs(0)
+    wcrop, frac = pick_crop(threads)
+    sd = make_state_dict(3)
+    calib = O.calib_vec(P2, P3)
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_step(sd, left, right, wcrop, rois3d, calib)
+    tot = 0.0
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        tot += cpu_port_step(sd, left, right, wcrop, rois3d, calib)
+    value = steps * (wcrop / W_NET) / tot
+    sample = ("oracle (CPU port of the reference path: torch-CPU fp32 forward + C decode/NMS/RoIAlign/dense_align), "
+              "600x%d crop per step (%.3f of a pair), %d timed steps" % (wcrop, wcrop / W_NET, steps))
+    out = {"impl": "reference", "metric": "stereo pairs/sec (1242x375)", "value": round(value, 5), "unit": "pairs/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps, "warmup": min(args.warmup, 1),
+           "ms_per_step": round(1e3 * tot / steps, 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": "configs[1] on host cores (reference CPU path; the reference's CUDA ops cannot be "
+                                  "built on this stack: torch.utils.ffi/THC are gone)", "parallelism": "cpu"},
+           "cpu_baseline": {"value": round(value, 5), "unit": "pairs/s", "cores": threads, "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": round(value, 5), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,6 +153,11 @@ int sb_test_decode(const float* rois_left, const float* rois_right, const float*
                    const float* right_prob, const float* im_info, int R, int n_classes, int grid,
                    float* pred_boxes_left, float* pred_boxes_right, float* dim_orien_out,
                    float* pred_kpts, sb_stream_t stream);
+/* per-class detection NMS (test_net.py:233-259), one image: scores [R,nc], boxes [R,4nc] (decoded left
+ * boxes); keeps RoIs with score[:,cls] > score_thresh, sorted by score, NMS(nms_thresh); keep[] (>= R
+ * ints) receives RoI indices in kept order, num_out the count.  R <= 512.                          */
+int sb_class_nms(const float* scores, const float* boxes, int R, int n_classes, int cls,
+                 float score_thresh, float nms_thresh, int* keep, int* num_out, sb_stream_t stream);
 /* L2 flush helper for benchmarks: writes `bytes` of scratch */
 int sb_fill(float* p, size_t n, float v, sb_stream_t stream);
 /* number of kernel launches issued by this library since load (bench "gpu_launches") */

@@ -204,6 +204,72 @@ test_decode_kernel(const float* __restrict__ rois_l, const float* __restrict__ r
     o[0] = __fdiv_rn(pk, sc); o[1] = ktype; o[2] = km; o[3] = __fdiv_rn(pl, sc); o[4] = __fdiv_rn(pr, sc);
 }
 
+
+// per-class detection NMS of test_net.py:233-259 in one CTA (R <= 512): threshold, sort by score
+// (desc, index asc), bitmask NMS, greedy scan; keep[] = RoI indices in kept order.
+__global__ void __launch_bounds__(512)
+class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int R, int nc, int cls,
+                 float score_thresh, float nms_thresh, int* __restrict__ keep, int* __restrict__ num) {
+    __shared__ unsigned long long keys[512];
+    __shared__ float4 sbox[512];
+    __shared__ unsigned long long mask[512][8];
+    __shared__ int n_valid;
+    const int t = threadIdx.x;
+    if (t == 0) n_valid = 0;
+    unsigned long long k = 0;
+    if (t < R) {
+        const float s = scores[(size_t)t * nc + cls];
+        if (s > score_thresh) {
+            unsigned int b = __float_as_uint(s);
+            b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+            k = ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)t);
+        }
+    }
+    keys[t] = k;
+    __syncthreads();
+    if (k) atomicAdd(&n_valid, 1);
+    for (int kk = 2; kk <= 512; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const int ixj = t ^ j;
+            if (ixj > t) {
+                const unsigned long long a = keys[t], b = keys[ixj];
+                const bool desc = (t & kk) == 0;
+                if (desc ? (a < b) : (a > b)) { keys[t] = b; keys[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    const int n = n_valid;
+    if (t < n) {
+        const int idx = (int)(0xFFFFFFFFu - (unsigned)(keys[t] & 0xFFFFFFFFu));
+        const float* bp = boxes + (size_t)idx * 4 * nc + 4 * cls;
+        sbox[t] = make_float4(bp[0], bp[1], bp[2], bp[3]);
+    }
+    __syncthreads();
+    const int words = (n + 63) >> 6;
+    if (t < n) {
+        const float4 cur = sbox[t];
+        for (int w = 0; w < words; ++w) {
+            unsigned long long bits = 0;
+            const int j0 = w * 64, j1 = min(n, j0 + 64);
+            for (int j = max(j0, t + 1); j < j1; ++j)
+                if (sb_iou(cur, sbox[j]) > nms_thresh) bits |= 1ULL << (j - j0);
+            mask[t][w] = bits;
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long remv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            if (!((remv[i >> 6] >> (i & 63)) & 1ULL)) {
+                keep[cnt++] = (int)(0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFu));
+                for (int w = i >> 6; w < words; ++w) remv[w] |= mask[i][w];
+            }
+        }
+        *num = cnt;
+    }
+}
+
 }  // namespace
 
 extern "C" int sb_fill(float* p, size_t n, float v, sb_stream_t stream) {
@@ -268,6 +334,15 @@ extern "C" int sb_test_decode(const float* rois_left, const float* rois_right, c
                                                                      kpts_prob, left_prob, right_prob, im_info, R,
                                                                      n_classes, grid, pred_boxes_left,
                                                                      pred_boxes_right, dim_orien_out, pred_kpts);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_class_nms(const float* scores, const float* boxes, int R, int n_classes, int cls,
+                            float score_thresh, float nms_thresh, int* keep, int* num_out, sb_stream_t stream) {
+    if (R < 0 || R > 512 || cls < 0 || cls >= n_classes || !keep || !num_out) return SB_EINVAL;
+    class_nms_kernel<<<1, 512, 0, sb_cs(stream)>>>(scores, boxes, R, n_classes, cls, score_thresh, nms_thresh, keep, num_out);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

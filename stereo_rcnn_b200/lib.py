@@ -66,6 +66,7 @@ _SIGS = {
                              c_void_p, c_void_p]),
     "sb_box_tail": (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p]),
     "sb_test_decode": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int] + [c_void_p] * 4 + [c_void_p]),
+    "sb_class_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "sb_fill": (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
 }
 

@@ -292,6 +292,17 @@ def test_decode(rois_left, rois_right, bbox_pred, dim_orien, kpts_prob, left_pro
     return pbl, pbr, do, pk
 
 
+def class_nms(scores, boxes_left, cls, score_thresh=0.05, nms_thresh=0.3):
+    """test_net.py:233-259 on device -> (keep [R] int32 RoI indices in kept order, num [1] int32)"""
+    L = _l.load()
+    R, nc = scores.shape
+    keep = torch.empty(R, dtype=torch.int32, device=scores.device)
+    num = torch.empty(1, dtype=torch.int32, device=scores.device)
+    check(L.sb_class_nms(ptr(_f32c(scores)), ptr(_f32c(boxes_left)), R, nc, int(cls), float(score_thresh),
+                         float(nms_thresh), ptr(keep), ptr(num), stream_ptr()), "sb_class_nms")
+    return keep, num
+
+
 def l2_flush(buf):
     L = _l.load()
     check(L.sb_fill(ptr(buf), buf.numel(), 0.0, stream_ptr()), "sb_fill")

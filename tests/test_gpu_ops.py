@@ -295,3 +295,21 @@ def test_dense_align_no_valid_pixel_early_out_and_module_api():
     np.testing.assert_array_equal(dis.cpu().numpy(), dis_o)          # dis_init, bit-exact
     st, dis = align_parallel(Calib, 1.0, cu(left)[None], cu(right)[None], cu(b[:0]), cu(k[:0]), cu(p[:0]))
     assert st.numel() == 0 and dis.numel() == 0
+
+
+def test_class_nms_vs_oracle():
+    rs = np.random.RandomState(8)
+    R = 300
+    scores = rs.rand(R, 2).astype(np.float32)
+    scores[::7, 1] = 0.01                                  # below eval_thresh
+    scores[5, 1] = scores[9, 1]                            # a tie
+    xy = rs.rand(R, 2) * 300
+    wh = rs.rand(R, 2) * 150 + 10
+    boxes = np.zeros((R, 8), np.float32)
+    boxes[:, 4:6], boxes[:, 6:8] = xy, xy + wh
+    keep, num = G.class_nms(cu(scores), cu(boxes), 1, 0.05, 0.3)
+    ref = O.per_class_nms(scores, boxes, 1, 0.05, 0.3)
+    assert int(num[0]) == ref.size
+    np.testing.assert_array_equal(keep[:ref.size].cpu().numpy(), ref)
+    keep, num = G.class_nms(cu(scores * 0), cu(boxes), 1, 0.05, 0.3)
+    assert int(num[0]) == 0
