@@ -69,7 +69,7 @@ int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W,
  * feats[l]: N x H_l x W_l x C (l = P2..P5); out[r][ph][pw][out_coff + c], row pitch out_ld floats. */
 int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* heights, const int* widths,
                               int C, float im_h, const float* rois, int R, int pooled,
-                              float* out, int out_ld, int out_coff, sb_stream_t stream);
+                              float* out, int out_ld, int out_coff, int round_tf32, sb_stream_t stream);
 
 /* ----------------------------------------------------- proposal layer ----
  * cls_prob [B,A,2] (column 1 = score), bbox_pred_lr [B,A,6], im_info [B,3] (device).
@@ -122,6 +122,14 @@ typedef struct {
     int N, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
     int in_ld, res_ld, UH, UW, relu;
     int out_coff;
+    /* TF32 operand hygiene (tcgen05 kind::tf32 TRUNCATES fp32 operands to 19 bits, a biased rounding):
+     *   out_mode 0: store exact fp32 (tensors read by non-conv consumers)
+     *   out_mode 1: store round-to-nearest TF32 (tensors read only by convs: truncation becomes exact)
+     *   out_mode 2: store exact fp32 with +0x1000 added to the bit pattern ("pre-biased"): the tensor
+     *               core's truncation then IS round-to-nearest, and exact readers subtract 0x1000 back
+     *               (residual stream of the trunk: conv input and exact residual from one tensor)
+     *   res_biased: the residual tensor is stored pre-biased;  in_biased: the input is (SIMT kernel only) */
+    int out_mode, res_biased, in_biased;
     long long out_n_stride, out_h_stride, out_w_stride;
 } sb_conv_desc;
 
@@ -132,7 +140,7 @@ int sb_conv2d_tc_supported(const sb_conv_desc* d);
 
 /* stem: NCHW image -> conv7x7/2 + frozen BN + ReLU -> NHWC (resnet.py:111-113) */
 int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[64][7][7][3]*/,
-                 const float* scale, const float* shift, float* out_nhwc, sb_stream_t stream);
+                 const float* scale, const float* shift, float* out_nhwc, int out_mode, sb_stream_t stream);
 /* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
 int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
 /* x[:, ::2, ::2, :] (stride-2 1x1 convs of resnet.py:71 and P6 of stereo_rcnn.py:39) */

@@ -84,6 +84,18 @@ __device__ __forceinline__ float sb_iou(const float4 a, const float4 b) {
     return __fdiv_rn(interS, __fsub_rn(__fadd_rn(Sa, Sb), interS));
 }
 
+// TF32 operand hygiene helpers (see sb_conv_desc.out_mode in the header)
+__device__ __forceinline__ float sb_round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float sb_bias_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ float sb_unbias_tf32(float x) { return __uint_as_float(__float_as_uint(x) - 0x1000u); }
+__device__ __forceinline__ float sb_store_mode(float x, int mode) {
+    return mode == 1 ? sb_round_tf32(x) : (mode == 2 ? sb_bias_tf32(x) : x);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -74,6 +74,10 @@ conv_simt_kernel(sb_conv_desc d) {
             const bool ok = a_ok[i] && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W;
             ra[i] = ok ? ld4(d.in + (a_base[i] + (long long)hi * d.W + wi) * d.in_ld + ci)
                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && d.in_biased) {
+                ra[i].x = sb_unbias_tf32(ra[i].x); ra[i].y = sb_unbias_tf32(ra[i].y);
+                ra[i].z = sb_unbias_tf32(ra[i].z); ra[i].w = sb_unbias_tf32(ra[i].w);
+            }
         }
         rb = b_ok ? ld4(d.wgt + (long long)b_co * wrow + (long long)tap * d.Cin + ci)
                   : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,7 +150,7 @@ conv_simt_kernel(sb_conv_desc d) {
         if (d.residual) {
             const float* r = d.residual + ((long long)(n * d.Ho + ho) * d.Wo + wo) * d.res_ld + c;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (c + j < d.Cout) v[j] += r[j];
+            for (int j = 0; j < 4; ++j) if (c + j < d.Cout) v[j] += d.res_biased ? sb_unbias_tf32(r[j]) : r[j];
         }
         if (d.up_src) {
             const float sy = __fmul_rn(rh, (float)ho), sx = __fmul_rn(rw, (float)wo);
@@ -166,6 +170,10 @@ conv_simt_kernel(sb_conv_desc d) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (d.out_mode) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = sb_store_mode(v[j], d.out_mode);
+        }
         float* o = d.out + (long long)n * d.out_n_stride + (long long)ho * d.out_h_stride +
                    (long long)wo * d.out_w_stride + d.out_coff + c;
         if (vec && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -182,7 +190,7 @@ conv_simt_kernel(sb_conv_desc d) {
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo,
             const float* __restrict__ wgt, const float* __restrict__ scale,
-            const float* __restrict__ shift, float* __restrict__ out) {
+            const float* __restrict__ shift, float* __restrict__ out, int out_mode) {
     __shared__ float ws[147][64];   // [tap*3+ci][co]
     for (int e = threadIdx.x; e < 147 * 64; e += 256) {
         int co = e / 147, k = e % 147;
@@ -223,6 +231,10 @@ stem_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo,
         v.y = fmaxf(__fadd_rn(__fmul_rn(acc[j + 1], scale[cq * 16 + j + 1]), shift[cq * 16 + j + 1]), 0.f);
         v.z = fmaxf(__fadd_rn(__fmul_rn(acc[j + 2], scale[cq * 16 + j + 2]), shift[cq * 16 + j + 2]), 0.f);
         v.w = fmaxf(__fadd_rn(__fmul_rn(acc[j + 3], scale[cq * 16 + j + 3]), shift[cq * 16 + j + 3]), 0.f);
+        if (out_mode) {
+            v.x = sb_store_mode(v.x, out_mode); v.y = sb_store_mode(v.y, out_mode);
+            v.z = sb_store_mode(v.z, out_mode); v.w = sb_store_mode(v.w, out_mode);
+        }
         *reinterpret_cast<float4*>(o + j) = v;
     }
 }
@@ -242,11 +254,11 @@ extern "C" int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream) {
 }
 
 extern "C" int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt, const float* scale,
-                            const float* shift, float* out_nhwc, sb_stream_t stream) {
+                            const float* shift, float* out_nhwc, int out_mode, sb_stream_t stream) {
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
     const long long M = (long long)N * Ho * Wo;
     if (M <= 0) return SB_EINVAL;
-    stem_kernel<<<sb_div_up(M, 64), 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, wgt, scale, shift, out_nhwc);
+    stem_kernel<<<sb_div_up(M, 64), 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, wgt, scale, shift, out_nhwc, out_mode);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

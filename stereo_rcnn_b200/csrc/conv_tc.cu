@@ -325,7 +325,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                         if (c + 3 < d.Cout) {
                             if (rrow) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(rrow + c);
+                                float4 r4 = *reinterpret_cast<const float4*>(rrow + c);
+                                if (d.res_biased) {
+                                    r4.x = sb_unbias_tf32(r4.x); r4.y = sb_unbias_tf32(r4.y);
+                                    r4.z = sb_unbias_tf32(r4.z); r4.w = sb_unbias_tf32(r4.w);
+                                }
                                 o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                             }
                             if (u00) {
@@ -342,16 +346,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                             }
+                            if (d.out_mode) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) o[e] = sb_store_mode(o[e], d.out_mode);
+                            }
                             *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
                             for (int e = 0; e < 4 && c + e < d.Cout; ++e) {
                                 float x = o[e];
-                                if (rrow) x += rrow[c + e];
+                                if (rrow) x += d.res_biased ? sb_unbias_tf32(rrow[c + e]) : rrow[c + e];
                                 if (u00)
                                     x += ly0 * (lx0 * u00[c + e] + lx1 * u01[c + e]) +
                                          ly1 * (lx0 * u10[c + e] + lx1 * u11[c + e]);
                                 if (d.relu) x = fmaxf(x, 0.f);
-                                orow[c + e] = x;
+                                orow[c + e] = sb_store_mode(x, d.out_mode);
                             }
                         }
                     }

@@ -131,7 +131,7 @@ __device__ __forceinline__ int roi_level(const float* roi) {
 // one CTA per (roi, output row ph); C % 4 == 0; dynamic smem = 2 * (P+1) * C floats
 __global__ void __launch_bounds__(256)
 roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int P,
-                       float* __restrict__ out, int out_ld, int out_coff) {
+                       float* __restrict__ out, int out_ld, int out_coff, int round_tf32) {
     extern __shared__ float4 lat[];  // [2][P+1][C/4]
     const int n = blockIdx.x, ph = blockIdx.y;
     const float* roi = rois + 5 * n;
@@ -168,6 +168,9 @@ roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int
         o.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, a1.y), __fadd_rn(b0.y, b1.y)), 0.25f);
         o.z = __fmul_rn(__fadd_rn(__fadd_rn(a0.z, a1.z), __fadd_rn(b0.z, b1.z)), 0.25f);
         o.w = __fmul_rn(__fadd_rn(__fadd_rn(a0.w, a1.w), __fadd_rn(b0.w, b1.w)), 0.25f);
+        if (round_tf32) {   // the pooled tile is read only by tensor-core convs: make TF32 truncation exact
+            o.x = sb_round_tf32(o.x); o.y = sb_round_tf32(o.y); o.z = sb_round_tf32(o.z); o.w = sb_round_tf32(o.w);
+        }
         *reinterpret_cast<float4*>(orow + (size_t)pw * out_ld + 4 * c4) = o;
     }
 }
@@ -202,7 +205,8 @@ extern "C" int sb_roi_align_backward(const float* top_grad, int N, int C, int H,
 
 extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* heights, const int* widths,
                                          int C, float im_h, const float* rois, int R, int pooled,
-                                         float* out, int out_ld, int out_coff, sb_stream_t stream) {
+                                         float* out, int out_ld, int out_coff, int round_tf32,
+                                         sb_stream_t stream) {
     if (R == 0) return SB_OK;
     if (R < 0 || (C & 3) || pooled < 1 || (out_ld & 3) || (out_coff & 3)) return SB_EINVAL;
     PyramidArgs a;
@@ -221,7 +225,7 @@ extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* h
         cur_max = smem;
     }
     dim3 grid(R, pooled);
-    roi_align_pyramid_nhwc<<<grid, 256, smem, sb_cs(stream)>>>(a, C, rois, pooled, out, out_ld, out_coff);
+    roi_align_pyramid_nhwc<<<grid, 256, smem, sb_cs(stream)>>>(a, C, rois, pooled, out, out_ld, out_coff, round_tf32);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -24,9 +24,14 @@ def _pack_conv(w):
 class PackedConv(object):
     __slots__ = ("w", "scale", "shift", "Cin", "Cout", "kh", "kw", "pad")
 
+    round_weights = True      # class-wide switch: False keeps exact fp32 weights (SIMT yardstick runs)
+
     def __init__(self, w, scale, shift, pad):
         self.Cout, self.Cin, self.kh, self.kw = w.shape
-        self.w, self.scale, self.shift, self.pad = _pack_conv(w), scale, shift, pad
+        wp = _pack_conv(w).clone()
+        if PackedConv.round_weights:   # round to TF32 (nearest) once: the tensor core would otherwise truncate
+            ops.round_tf32_(wp)
+        self.w, self.scale, self.shift, self.pad = wp, scale, shift, pad
 
 
 class StereoRCNNEngine(object):
@@ -37,6 +42,9 @@ class StereoRCNNEngine(object):
         self.n_classes = n_classes
         self.conv_impl = conv_impl
         self.impl_used = {}
+        # conv_impl="simt" is the exact-fp32 yardstick: exact weights, exact stores, no TF32 hygiene modes
+        self.exact = conv_impl == "simt"
+        PackedConv.round_weights = not self.exact
         sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
               if not k.endswith("num_batches_tracked")}
         self.p = {}
@@ -93,15 +101,18 @@ class StereoRCNNEngine(object):
 
     # ------------------------------------------------------------------ helpers
     def _conv(self, x, pc, relu=False, stride=1, residual=None, up_src=None, out=None, out_coff=0,
-              out_strides=None, Cin=None, tag=None):
+              out_strides=None, Cin=None, tag=None, out_mode=ops.EXACT, res_biased=False, in_biased=False):
         N, H, W = x.shape[:3]
         Ho = (H + 2 * pc.pad - pc.kh) // stride + 1
         Wo = (W + 2 * pc.pad - pc.kw) // stride + 1
         if out is None:
             out = torch.empty(N, Ho, Wo, pc.Cout, dtype=torch.float32, device=x.device)
+        if self.exact:
+            out_mode, res_biased, in_biased = ops.EXACT, False, False
         d = ops.conv_desc(x, pc.w, out, pc.Cin if Cin is None else Cin, pc.Cout, pc.kh, pc.kw, stride, pc.pad,
                           Ho, Wo, scale=pc.scale, shift=pc.shift, residual=residual, up_src=up_src, relu=relu,
-                          out_coff=out_coff, out_strides=out_strides)
+                          out_coff=out_coff, out_strides=out_strides, out_mode=out_mode, res_biased=res_biased,
+                          in_biased=in_biased)
         impl = ops.conv2d(d, self.conv_impl)
         if tag is not None:
             self.impl_used[tag] = impl
@@ -109,27 +120,36 @@ class StereoRCNNEngine(object):
 
     def _bottleneck(self, x, prefix, stride, has_ds):
         """resnet.py:82-102; the stride sits on the 1x1 conv1 and on the downsample (Q1)"""
+        # TF32 hygiene: the residual stream x is stored "pre-biased" (exact fp32 + 0x1000): the tensor core's
+        # truncation of it is then round-to-nearest, and the residual add un-biases it exactly.  Tensors
+        # read only by the next conv (o1, o2) are stored rounded to TF32.
         xin = ops.subsample2(x) if stride == 2 else x
-        o = self._conv(xin, self.p[prefix + ".conv1"], relu=True, tag=prefix + ".conv1")
-        o = self._conv(o, self.p[prefix + ".conv2"], relu=True, tag=prefix + ".conv2")
-        res = self._conv(xin, self.p[prefix + ".downsample.0"], tag=prefix + ".ds") if has_ds else x
-        return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3")
+        o = self._conv(xin, self.p[prefix + ".conv1"], relu=True, tag=prefix + ".conv1", out_mode=ops.ROUND_TF32,
+                       in_biased=True)
+        o = self._conv(o, self.p[prefix + ".conv2"], relu=True, tag=prefix + ".conv2", out_mode=ops.ROUND_TF32)
+        if has_ds:
+            res = self._conv(xin, self.p[prefix + ".downsample.0"], tag=prefix + ".ds", in_biased=True)
+        else:
+            res = x
+        return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3",
+                          out_mode=ops.BIASED, res_biased=not has_ds)
 
     def trunk_fpn(self, im_nchw):
         """images [N,3,H,W] NCHW -> dict of NHWC C2..C5, P2..P6 (stereo_rcnn.py:155-168)"""
-        c1 = ops.maxpool3x3s2_ceil(ops.stem_conv(im_nchw, *self.stem))
+        c1 = ops.maxpool3x3s2_ceil(ops.stem_conv(im_nchw, *self.stem, out_mode=ops.EXACT if self.exact else ops.BIASED))   # max() keeps the bias
         feats = {"c1": c1}
         x = c1
         for li, nb in enumerate(LAYERS):
             for bi in range(nb):
                 x = self._bottleneck(x, "RCNN_layer%d.0.%d" % (li + 1, bi), STRIDES[li] if bi == 0 else 1, bi == 0)
             feats["c%d" % (li + 2)] = x
-        p5 = self._conv(feats["c5"], self.p["RCNN_toplayer"], tag="toplayer")
-        t = self._conv(feats["c4"], self.p["RCNN_latlayer1"], up_src=p5, tag="lat1")     # lateral + upsample-add
-        p4 = self._conv(t, self.p["RCNN_smooth1"], tag="smooth1")
-        t = self._conv(feats["c3"], self.p["RCNN_latlayer2"], up_src=p4, tag="lat2")
+        R = ops.ROUND_TF32
+        p5 = self._conv(feats["c5"], self.p["RCNN_toplayer"], tag="toplayer", in_biased=True)
+        t = self._conv(feats["c4"], self.p["RCNN_latlayer1"], up_src=p5, tag="lat1", out_mode=R, in_biased=True)
+        p4 = self._conv(t, self.p["RCNN_smooth1"], tag="smooth1")          # lateral + upsample-add fused above
+        t = self._conv(feats["c3"], self.p["RCNN_latlayer2"], up_src=p4, tag="lat2", out_mode=R, in_biased=True)
         p3 = self._conv(t, self.p["RCNN_smooth2"], tag="smooth2")
-        t = self._conv(feats["c2"], self.p["RCNN_latlayer3"], up_src=p3, tag="lat3")
+        t = self._conv(feats["c2"], self.p["RCNN_latlayer3"], up_src=p3, tag="lat3", out_mode=R, in_biased=True)
         p2 = self._conv(t, self.p["RCNN_smooth3"], tag="smooth3")
         p6 = ops.subsample2(p5)                                                           # Q5
         feats.update(p2=p2, p3=p3, p4=p4, p5=p5, p6=p6)
@@ -147,7 +167,8 @@ class StereoRCNNEngine(object):
             cat = torch.empty(B, h, w, 1024, dtype=torch.float32, device=dev)
             for side in range(2):   # shared RPN_Conv on L then R, channel-concatenated (Q6)
                 self._conv(f[side * B:(side + 1) * B], self.p["RCNN_rpn.RPN_Conv"], relu=True, out=cat,
-                           out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv")
+                           out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv",
+                           out_mode=ops.ROUND_TF32)
             self._conv(cat, self.p["rpn_heads"], out=head[:, off:off + h * w],
                        out_strides=(P * 32, w * 32, 32), tag="rpn_heads")
             off += h * w
@@ -162,15 +183,16 @@ class StereoRCNNEngine(object):
         R = rois_l.shape[0]
         dev = self.device
         pooled = torch.empty(R, 7, 7, 512, dtype=torch.float32, device=dev)
-        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0)
-        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256)
-        x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0")
+        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0, round_tf32=not self.exact)
+        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256, round_tf32=not self.exact)
+        x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0",
+                       out_mode=ops.ROUND_TF32)
         fc7 = self._conv(x, self.p["RCNN_top.3"], relu=True, tag="top3").view(R, 2048)
         cls_prob, bbox, dim = ops.box_tail(fc7, *self.fc, n_classes=self.n_classes)
-        pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14)
+        pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14, round_tf32=not self.exact)
         x = pk
         for i in range(0, 12, 2):
-            x = self._conv(x, self.p["RCNN_kpts.%d" % i], relu=True, tag="kpts%d" % i)
+            x = self._conv(x, self.p["RCNN_kpts.%d" % i], relu=True, tag="kpts%d" % i, out_mode=ops.ROUND_TF32)
         up = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
         for a in range(2):
             for b in range(2):
@@ -198,6 +220,7 @@ class StereoRCNNEngine(object):
         out["cls_prob"] = out["cls_prob"].view(B, n, -1)
         out["bbox_pred"] = out["bbox_pred"].view(B, n, -1)
         out["dim_orien_pred"] = out["dim_orien_pred"].view(B, n, -1)
-        if keep_features:
-            out["feats"] = feats
+        if keep_features:      # debugging / tests: exact-fp32 views of the pre-biased trunk tensors
+            out["feats"] = {k: (ops.unbias(v) if (k[0] == "c" and not self.exact) else v) for k, v in feats.items()}
+            out["feats_raw"] = feats
         return out

@@ -94,7 +94,7 @@ def roi_align_backward(ah, aw, scale, top_grad, rois, bottom_grad):
     return 1
 
 
-def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0):
+def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0, round_tf32=False):
     """feats: 4 NHWC tensors (P2..P5); rois [R,5]; -> out [R,pooled,pooled,out_ld] NHWC"""
     L = _l.load()
     C = feats[0].shape[3]
@@ -105,7 +105,8 @@ def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0):
     hs = (ctypes.c_int * 4)(*[f.shape[1] for f in feats])
     ws_ = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
     check(L.sb_roi_align_pyramid_nhwc(fp, hs, ws_, C, float(im_h), ptr(_f32c(rois)), R, pooled, ptr(out),
-                                      out.shape[3], out_coff, stream_ptr()), "sb_roi_align_pyramid_nhwc")
+                                      out.shape[3], out_coff, 1 if round_tf32 else 0, stream_ptr()),
+          "sb_roi_align_pyramid_nhwc")
     return out
 
 
@@ -185,7 +186,8 @@ def dense_align(calib4, scale, im_left, im_right, box_left, keypoints, poses):
 
 # ------------------------------------------------------------- layer ops ----
 def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, shift=None, residual=None,
-              up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None):
+              up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None, out_mode=0, res_biased=False,
+              in_biased=False):
     """x: NHWC [N,H,W,in_ld]; wgt packed [Cout,kh,kw,Cin]; out: any tensor addressed through out_strides
     = (n, h, w) strides in floats (default: dense NHWC of out.shape[-1] channels)."""
     d = ConvDesc()
@@ -202,6 +204,7 @@ def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, s
     d.UH, d.UW = (up_src.shape[1], up_src.shape[2]) if up_src is not None else (0, 0)
     d.relu = 1 if relu else 0
     d.out_coff = out_coff
+    d.out_mode, d.res_biased, d.in_biased = int(out_mode), int(bool(res_biased)), int(bool(in_biased))
     if out_strides is None:
         ld = out.shape[-1]
         out_strides = (Ho * Wo * ld, Wo * ld, ld)
@@ -220,13 +223,13 @@ def conv2d(desc, impl="auto"):
     return impl
 
 
-def stem_conv(im_nchw, wgt, scale, shift):
+def stem_conv(im_nchw, wgt, scale, shift, out_mode=0):
     L = _l.load()
     N, _, H, W = im_nchw.shape
     Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     out = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=im_nchw.device)
-    check(L.sb_stem_conv(ptr(_f32c(im_nchw)), N, H, W, ptr(wgt), ptr(scale), ptr(shift), ptr(out), stream_ptr()),
-          "sb_stem_conv")
+    check(L.sb_stem_conv(ptr(_f32c(im_nchw)), N, H, W, ptr(wgt), ptr(scale), ptr(shift), ptr(out), int(out_mode),
+                         stream_ptr()), "sb_stem_conv")
     return out
 
 
@@ -310,3 +313,18 @@ def l2_flush(buf):
 
 def launch_count():
     return int(_l.load().sb_launch_count())
+
+
+EXACT, ROUND_TF32, BIASED = 0, 1, 2          # sb_conv_desc.out_mode
+
+
+def round_tf32_(w):
+    """in-place round-to-nearest (ties away) of fp32 values to TF32 precision (weights, once at pack time)"""
+    b = w.view(torch.int32)
+    b.add_(0x1000).bitwise_and_(~0x1FFF)
+    return w
+
+
+def unbias(x):
+    """exact fp32 view of a tensor stored pre-biased (out_mode 2); debugging / tests only"""
+    return (x.view(torch.int32) - 0x1000).view(torch.float32)
