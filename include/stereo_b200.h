@@ -141,6 +141,9 @@ int sb_conv2d_tc_supported(const sb_conv_desc* d);
 /* stem: NCHW image -> conv7x7/2 + frozen BN + ReLU -> NHWC (resnet.py:111-113) */
 int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[64][7][7][3]*/,
                  const float* scale, const float* shift, float* out_nhwc, int out_mode, sb_stream_t stream);
+/* stem as a tensor-core GEMM: patch matrix [N*Ho*Wo][160] (k = (r*7+s)*3+ci, zero padded from 147) that
+ * sb_conv2d_tc then multiplies with the [64][160] stem weights (1x1 conv, Cin = 160)              */
+int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream);
 /* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
 int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
 /* x[:, ::2, ::2, :] (stride-2 1x1 convs of resnet.py:71 and P6 of stereo_rcnn.py:39) */

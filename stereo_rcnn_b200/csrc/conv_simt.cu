@@ -239,7 +239,48 @@ stem_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo,
     }
 }
 
+// stem im2col: NCHW image -> rows of the 7x7/2 pad-3 patch matrix [M = N*Ho*Wo][160] with
+// k = (r*7+s)*3 + ci for k < 147 and zero padding up to 160 (a multiple of the 32-wide K tile of
+// the tcgen05 kernel).  One thread = one float4 (4 consecutive k) of one output pixel.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo, float4* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * 40;
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const int g = (int)(e % 40);
+    long long t = e / 40;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float* base = im + (long long)n * 3 * H * W;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = g * 4 + j;
+        float x = 0.f;
+        if (k < 147) {
+            const int tap = k / 3, ci = k - tap * 3;
+            const int r = tap / 7, s2 = tap - r * 7;
+            const int hi = ho * 2 - 3 + r, wi = wo * 2 - 3 + s2;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+                x = sb_round_tf32(__ldg(base + ((long long)ci * H + hi) * W + wi));   // RN, not the MMA's truncation
+        }
+        v[j] = x;
+    }
+    out[e] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 }  // namespace
+
+extern "C" int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream) {
+    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    const long long total = (long long)N * Ho * Wo * 40;
+    if (total <= 0) return SB_EINVAL;
+    stem_im2col_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, (float4*)out);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
 
 extern "C" int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream) {
     if (!d || !d->in || !d->wgt || !d->out) return SB_EINVAL;

@@ -16,7 +16,8 @@
 //     padding halo, so im2col never exists in memory).  128-byte swizzle, 1024-byte aligned
 //     stages, one 128-byte row (= 32 fp32 = BLOCK_K) per pixel per stage.
 //   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA
-//     issuer (one elected lane) + TMEM allocator, warps 2..5 = epilogue.  Three mbarrier
+//     issuer (one elected lane) + TMEM allocator, warps 2..9 = epilogue (two warps per TMEM lane
+//     quarter, each taking half of the tile's columns).  Three mbarrier
 //     pipelines: smem full/empty (kStages deep), TMEM full/empty (two accumulator stages, so
 //     the epilogue of tile i overlaps the main loop of tile i+1).
 //   * fused epilogue straight out of TMEM (`tcgen05.ld.32x32b.x32`): folded frozen-BN
@@ -32,7 +33,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;   // fp32 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;     // tf32
 constexpr int TW = 16, TH = 8;  // spatial patch of a 3x3 tile (TW*TH == BLOCK_M)
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
+constexpr int kMaxCout = 2048;   // scale/shift staged in shared memory
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,8 +126,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
@@ -164,6 +167,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tfull = empty + kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [Cout rounded up to BLOCK_N]
+    float* s_shift = s_scale + kMaxCout;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const sb_conv_desc& d = p.d;
@@ -175,13 +180,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) {
         if (elect_one()) {
             for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kNumEpiWarps); }
             fence_barrier_init();
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    {   // folded-BN scale / shift (or bias) for every output channel, once per (persistent) CTA
+        const int cpad = p.num_n_tiles * BLOCK_N;
+        for (int c = threadIdx.x; c < cpad; c += kNumThreads) {
+            s_scale[c] = (d.scale && c < d.Cout) ? d.scale[c] : 1.f;
+            s_shift[c] = (d.shift && c < d.Cout) ? d.shift[c] : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -254,9 +266,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share each lane quarter and
+        // split the tile's columns in halves.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;          // accumulator row == pixel inside the tile
+        constexpr int kColsPerWarp = BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32;
+        const int col_begin = half * kColsPerWarp;
+        const bool has_cols = col_begin < BLOCK_N;
         int acc = 0;
         uint32_t acc_phase = 0;
         float rh = 0.f, rw = 0.f;
@@ -266,7 +284,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
-            // decode this thread's output pixel
             int n_img, ho, wo;
             bool valid;
             if (p.patch) {
@@ -304,33 +321,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            if (has_cols) {
 #pragma unroll 1
-            for (int cc = 0; cc < BLOCK_N; cc += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc), v);
-                const int cbase = nt * BLOCK_N + cc;
-                if (valid && cbase < d.Cout) {
+                for (int cc = col_begin; cc < col_begin + kColsPerWarp; cc += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc), v);
+                    const int cbase = nt * BLOCK_N + cc;
+                    const bool chunk_live = valid && cbase < d.Cout;
+                    const bool full = cbase + 31 < d.Cout;
+                    // issue the residual loads before waiting on TMEM
+                    float4 r4[8];
+                    if (chunk_live && rrow && full) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int c = cbase + j;
-                        if (c >= d.Cout) break;
-                        float o[4];
+                        for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(rrow + cbase + 4 * j);
+                    }
+                    tmem_ld_wait();
+                    if (chunk_live && full) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float x = __uint_as_float(v[j + e]);
-                            const bool in = c + e < d.Cout;
-                            const float sc = (d.scale && in) ? __ldg(d.scale + c + e) : 1.f;
-                            const float sh = (d.shift && in) ? __ldg(d.shift + c + e) : 0.f;
-                            o[e] = __fadd_rn(__fmul_rn(x, sc), sh);
-                        }
-                        if (c + 3 < d.Cout) {
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = cbase + 4 * j;
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+                            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+                            float o[4];
+                            o[0] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 0]), sc.x), sh.x);
+                            o[1] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 1]), sc.y), sh.y);
+                            o[2] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 2]), sc.z), sh.z);
+                            o[3] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 3]), sc.w), sh.w);
                             if (rrow) {
-                                float4 r4 = *reinterpret_cast<const float4*>(rrow + c);
+                                float4 r = r4[j];
                                 if (d.res_biased) {
-                                    r4.x = sb_unbias_tf32(r4.x); r4.y = sb_unbias_tf32(r4.y);
-                                    r4.z = sb_unbias_tf32(r4.z); r4.w = sb_unbias_tf32(r4.w);
+                                    r.x = sb_unbias_tf32(r.x); r.y = sb_unbias_tf32(r.y);
+                                    r.z = sb_unbias_tf32(r.z); r.w = sb_unbias_tf32(r.w);
                                 }
-                                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                                o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
                             }
                             if (u00) {
                                 const float4 a = *reinterpret_cast<const float4*>(u00 + c);
@@ -351,23 +374,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                 for (int e = 0; e < 4; ++e) o[e] = sb_store_mode(o[e], d.out_mode);
                             }
                             *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
-                            for (int e = 0; e < 4 && c + e < d.Cout; ++e) {
-                                float x = o[e];
-                                if (rrow) x += d.res_biased ? sb_unbias_tf32(rrow[c + e]) : rrow[c + e];
-                                if (u00)
-                                    x += ly0 * (lx0 * u00[c + e] + lx1 * u01[c + e]) +
-                                         ly1 * (lx0 * u10[c + e] + lx1 * u11[c + e]);
-                                if (d.relu) x = fmaxf(x, 0.f);
-                                orow[c + e] = sb_store_mode(x, d.out_mode);
-                            }
+                        }
+                    } else if (chunk_live) {
+                        // ragged tail of the channel range (Cout not a multiple of 32): scalar path
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int c = cbase + j;
+                            if (c >= d.Cout) continue;
+                            float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c]), s_shift[c]);
+                            if (rrow) x += d.res_biased ? sb_unbias_tf32(rrow[c]) : rrow[c];
+                            if (u00)
+                                x += ly0 * (lx0 * u00[c] + lx1 * u01[c]) + ly1 * (lx0 * u10[c] + lx1 * u11[c]);
+                            if (d.relu) x = fmaxf(x, 0.f);
+                            orow[c] = sb_store_mode(x, d.out_mode);
                         }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);   // 4 epilogue warps -> count 4
+            if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -413,7 +439,7 @@ int pick_block_n(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128); }
 
 template <int BN, int ST>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256;
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -443,6 +469,7 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
     const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0;
     const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1;
     if (!k1 && !k3) return 0;
+    if (d->Cout > kMaxCout) return 0;
     if ((reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->wgt) & 15) ||
         (reinterpret_cast<uintptr_t>(d->out) & 15))
         return 0;
@@ -493,6 +520,6 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     switch (BN) {
         case 32: return launch<32, 8>(ma, mb, p, st);
         case 64: return launch<64, 8>(ma, mb, p, st);
-        default: return launch<128, 6>(ma, mb, p, st);
+        default: return launch<128, 5>(ma, mb, p, st);
     }
 }

@@ -63,6 +63,9 @@ class StereoRCNNEngine(object):
         # stem: [64,3,7,7] -> [64][7][7][3]
         s, b = bn_fold("RCNN_layer0.1")
         self.stem = (_pack_conv(sd["RCNN_layer0.0.weight"]), s, b)
+        wst = torch.zeros(64, 160, 1, 1, device=self.device)          # stem as a GEMM over the padded patch matrix
+        wst[:, :147, 0, 0] = self.stem[0].reshape(64, 147)
+        self.p["stem_gemm"] = PackedConv(wst, s, b, 0)
         for li, nb in enumerate(LAYERS):
             for bi in range(nb):
                 p = "RCNN_layer%d.0.%d" % (li + 1, bi)
@@ -136,7 +139,11 @@ class StereoRCNNEngine(object):
 
     def trunk_fpn(self, im_nchw):
         """images [N,3,H,W] NCHW -> dict of NHWC C2..C5, P2..P6 (stereo_rcnn.py:155-168)"""
-        c1 = ops.maxpool3x3s2_ceil(ops.stem_conv(im_nchw, *self.stem, out_mode=ops.EXACT if self.exact else ops.BIASED))   # max() keeps the bias
+        if self.exact:
+            c0 = ops.stem_conv(im_nchw, *self.stem, out_mode=ops.EXACT)
+        else:       # patch matrix (pixels rounded to TF32) + tcgen05 GEMM
+            c0 = self._conv(ops.stem_im2col(im_nchw), self.p["stem_gemm"], relu=True, out_mode=ops.BIASED, tag="stem")
+        c1 = ops.maxpool3x3s2_ceil(c0)                      # max() commutes with the monotone pre-bias
         feats = {"c1": c1}
         x = c1
         for li, nb in enumerate(LAYERS):

@@ -233,6 +233,16 @@ def stem_conv(im_nchw, wgt, scale, shift, out_mode=0):
     return out
 
 
+def stem_im2col(im_nchw):
+    """-> [N, Ho, Wo, 160] patch matrix of the 7x7/2 stem (147 taps zero-padded to 160)"""
+    L = _l.load()
+    N, _, H, W = im_nchw.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty(N, Ho, Wo, 160, dtype=torch.float32, device=im_nchw.device)
+    check(L.sb_stem_im2col(ptr(_f32c(im_nchw)), N, H, W, ptr(out), stream_ptr()), "sb_stem_im2col")
+    return out
+
+
 def maxpool3x3s2_ceil(x):
     L = _l.load()
     N, H, W, C = x.shape

@@ -33,6 +33,9 @@ def main():
         print("%-6s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(got[0:1], o["left"][k].numpy())))
     for k in ("rpn_cls_prob", "rpn_bbox_pred"):
         print("%-14s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(r[k].cpu().numpy(), o[k].numpy())))
+    a = {tuple(np.round(x, 1)) for x in r["rois_left"][0].cpu().numpy()}
+    b = {tuple(np.round(x, 1)) for x in o["rois_left"][0].numpy()}
+    print("end-to-end proposal set overlap %.3f" % (len(a & b) / float(len(b))))
     h = eng.heads(r["feats_raw"], 1, o["rois_left"].cuda().view(-1, 5), o["rois_right"].cuda().view(-1, 5), float(H))
     torch.cuda.synchronize()
     for k in ("pooled_box", "pooled_kpts"):
