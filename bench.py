@@ -90,7 +90,8 @@ class Pipeline(object):
     """the call a user makes: images in -> detection record + refined disparities out"""
 
     def __init__(self, device):
-        from stereo_rcnn_b200 import engine, ops
+        from stereo_rcnn_b200 import engine, ops, parallel
+        self.par = parallel
         from stereo_rcnn_b200.synth import make_state_dict
         self.ops, self.dev = ops, device
         self.eng = engine.StereoRCNNEngine(make_state_dict(3), device)
@@ -104,7 +105,7 @@ class Pipeline(object):
                                              o["right_border_prob"], self.info[0])
         keep, nkeep = ops.class_nms(o["cls_prob"][0], pbl, 1, 0.05, 0.3)
         st, dis = ops.dense_align(calib4, SCALE32, iml, imr, *rois3d)
-        rec = torch.cat((o["cls_prob"][0], pbl, pbr, dimo, pk), 1)            # [300, 33] detection record
+        rec = self.par.detection_record(o["cls_prob"][0], pbl, pbr, dimo, pk)   # [300, 33]
         return rec, keep, nkeep, st, dis
 
 
@@ -137,7 +138,7 @@ def run_ours(args):
     def step_resident():
         rec, keep, nkeep, st, dis = pipe.step(iml, imr, calib4, rois3d)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rec)
+            pipe.par.gather_records(rec, world, dist, out=gathered)
         return rec, dis
 
     def step_e2e():
@@ -145,7 +146,7 @@ def run_ours(args):
         c = host_r.to(dev, non_blocking=True)
         rec, keep, nkeep, st, dis = pipe.step(a, c, calib4, rois3d)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, rec)
+            pipe.par.gather_records(rec, world, dist, out=gathered)
         host_rec.copy_(rec, non_blocking=True)
         host_dis.copy_(dis, non_blocking=True)
         return rec, dis
@@ -167,12 +168,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        total_ms = sum(s.elapsed_time(e) for s, e in ev)
-        if world > 1:
-            t = torch.tensor([total_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t[0])
-        return total_ms
+        return pipe.par.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), dev, world, dist)
 
     sampler = ClockSampler(local)
     sampler.start()
