@@ -135,16 +135,33 @@ def run_ours(args):
     host_rec = torch.empty(N_ROIS, REC_COLS).pin_memory()
     host_dis = torch.empty(D_ALIGN).pin_memory()
 
+    use_graph = os.environ.get("SB_GRAPH", "1") != "0"
+    if use_graph:
+        # the ~170 launches of one step are captured once into a CUDA graph (no tracing compiler: the graph
+        # is the literal launch sequence of our kernels) and replayed; inputs live in fixed device buffers
+        from stereo_rcnn_b200.engine import GraphRunner
+        runner = GraphRunner(lambda a, c: pipe.step(a, c, calib4, rois3d), [iml, imr])
+
+    def run_step(a, c):
+        if use_graph:
+            return runner()
+        return pipe.step(a, c, calib4, rois3d)
+
     def step_resident():
-        rec, keep, nkeep, st, dis = pipe.step(iml, imr, calib4, rois3d)
+        rec, keep, nkeep, st, dis = run_step(iml, imr)
         if world > 1:
             pipe.par.gather_records(rec, world, dist, out=gathered)
         return rec, dis
 
     def step_e2e():
-        a = host_l.to(dev, non_blocking=True)
-        c = host_r.to(dev, non_blocking=True)
-        rec, keep, nkeep, st, dis = pipe.step(a, c, calib4, rois3d)
+        if use_graph:
+            iml.copy_(host_l, non_blocking=True)
+            imr.copy_(host_r, non_blocking=True)
+            rec, keep, nkeep, st, dis = runner()
+        else:
+            a = host_l.to(dev, non_blocking=True)
+            c = host_r.to(dev, non_blocking=True)
+            rec, keep, nkeep, st, dis = pipe.step(a, c, calib4, rois3d)
         if world > 1:
             pipe.par.gather_records(rec, world, dist, out=gathered)
         host_rec.copy_(rec, non_blocking=True)
@@ -173,8 +190,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.launch_count()
+    pipe.step(iml, imr, calib4, rois3d)                 # one eager step only to count our kernel launches
+    launches = ops.launch_count() - l0
     total_ms = timed(step_resident, args.steps, max(args.warmup, 3))
-    launches = (ops.launch_count() - l0) // (args.steps + max(args.warmup, 3))
     e2e_ms = timed(step_e2e, args.steps, 1)
     sampler.stop_flag = True
     ms_per_step = total_ms / args.steps
@@ -209,7 +227,7 @@ def run_ours(args):
         "config": {"workload": "configs[1]: batch-1 inference per GPU, synthetic KITTI-shape pair 2x[1,3,600,1987], "
                                "full pipeline incl. dense_align (D=%d synthetic poses)" % D_ALIGN,
                    "weights": "seeded variance-preserving random init (stereo_rcnn_b200.synth.make_state_dict(3))",
-                   "l2": "256 MB flush between timed iterations", "parallelism": "dp%d (1 pair/rank)" % world},
+                   "l2": "256 MB flush between timed iterations", "cuda_graph": use_graph, "parallelism": "dp%d (1 pair/rank)" % world},
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s",
                 "h2d_bytes_per_step": int(host_l.numel() * 4 * 2),
                 "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},

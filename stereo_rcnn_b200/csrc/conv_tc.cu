@@ -24,6 +24,7 @@
 //     scale/shift or bias, residual add, FPN bilinear (align_corners) upsample-add, ReLU,
 //     strided / channel-offset stores (RPN L/R concat, deconv scatter).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -435,7 +436,17 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
     return r == CUDA_SUCCESS;
 }
 
-int pick_block_n(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : 128); }
+// Tile-width choice.  One SM ingests ~64 B/clk from L2, so a K-step costs max(MMA cycles, bytes/64):
+//   BN=128: max(256, (16+16) KB / 64) = 512 cycles     BN=256: max(512, (16+32) KB / 64) = 768 cycles
+// and the persistent grid runs ceil(tiles/SMs) waves.  Pick the cheaper of the two for Cout >= 256.
+int pick_block_n(int cout, long long m_tiles, int num_sms) {
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    if (cout < 256) return 128;
+    const long long t128 = m_tiles * ((cout + 127) / 128), t256 = m_tiles * ((cout + 255) / 256);
+    const long long c128 = ((t128 + num_sms - 1) / num_sms) * 512, c256 = ((t256 + num_sms - 1) / num_sms) * 768;
+    return c256 <= c128 ? 256 : 128;
+}
 
 template <int BN, int ST>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
@@ -487,23 +498,29 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     p.patch = (d->kh == 3) ? 1 : 0;
     p.M = (long long)d->N * d->Ho * d->Wo;
     if (p.M == 0) return SB_OK;
-    const int BN = pick_block_n(d->Cout);
-    p.num_n_tiles = (d->Cout + BN - 1) / BN;
     p.kblocks_per_tap = d->Cin / BLOCK_K;
     p.num_k_blocks = d->kh * d->kw * p.kblocks_per_tap;
+    p.tiles_w = (d->W + TW - 1) / TW;
+    p.tiles_h = (d->H + TH - 1) / TH;
+    p.num_m_tiles = p.patch ? d->N * p.tiles_h * p.tiles_w : (int)((p.M + BLOCK_M - 1) / BLOCK_M);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    int BN = pick_block_n(d->Cout, p.num_m_tiles, sms);
+    if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256) BN = v; }
+    p.num_n_tiles = (d->Cout + BN - 1) / BN;
     CUtensorMap ma, mb;
     if (p.patch) {
-        p.tiles_w = (d->W + TW - 1) / TW;
-        p.tiles_h = (d->H + TH - 1) / TH;
-        p.num_m_tiles = d->N * p.tiles_h * p.tiles_w;
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
         cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 4, (cuuint64_t)d->W * d->in_ld * 4,
                                  (cuuint64_t)d->H * d->W * d->in_ld * 4};
         cuuint32_t box[4] = {BLOCK_K, TW, TH, 1};
         if (!make_map(&ma, d->in, 4, dims, strides, box)) return SB_EINVAL;
     } else {
-        p.tiles_w = p.tiles_h = 0;
-        p.num_m_tiles = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
         cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)d->in_ld * 4};
         cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
@@ -520,6 +537,7 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     switch (BN) {
         case 32: return launch<32, 8>(ma, mb, p, st);
         case 64: return launch<64, 8>(ma, mb, p, st);
+        case 256: return launch<256, 4>(ma, mb, p, st);
         default: return launch<128, 5>(ma, mb, p, st);
     }
 }

@@ -231,3 +231,29 @@ class StereoRCNNEngine(object):
             out["feats"] = {k: (ops.unbias(v) if (k[0] == "c" and not self.exact) else v) for k, v in feats.items()}
             out["feats_raw"] = feats
         return out
+
+
+class GraphRunner(object):
+    """Capture a launch-bound sequence of libstereo_b200 kernels once into a CUDA graph and replay it.
+
+    `fn(*static_inputs)` must be free of host<->device syncs (every entry point of the C ABI is) and is run
+    `warmup` times eagerly first so that workspaces, function attributes and TMA descriptors exist.  Inputs are
+    fixed tensors: copy new data into them (`runner.inputs[i].copy_(...)`) before `runner()`.
+    """
+
+    def __init__(self, fn, inputs, warmup=2):
+        self.fn, self.inputs = fn, list(inputs)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn(*self.inputs)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(*self.inputs)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.outputs

@@ -115,6 +115,8 @@ TC_CASES = [
     (1, 2048, 19, 63, 256, 1),
     (1, 256, 38, 125, 512, 3),
     (300, 25088, 1, 1, 2048, 1),
+    (2, 1024, 38, 125, 256, 1),      # 75 m-tiles: the wave model picks BLOCK_N = 256
+    (2, 256, 38, 125, 1024, 1),
 ]
 
 
