@@ -143,6 +143,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------ kernel
+struct RowInfo {          // per accumulator row of the current tile (one per lane, in shared memory)
+    long long out_off, res_off, up_off;
+    float ly1, lx1;
+    int flags;            // bit0 valid pixel, bit1 / bit2: the bilinear tap has a +1 row / column
+    int pad;
+};
+
+constexpr size_t kEpiSmem = (size_t)kNumEpiWarps * (32 * 8 * 16 + 32 * sizeof(RowInfo));
+
 struct TcParams {
     sb_conv_desc d;
     int patch;            // 0: flat [M,Cin] rows (1x1), 1: 8x16 spatial patches (3x3 / pad 1)
@@ -153,7 +162,7 @@ struct TcParams {
     long long M;
 };
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p) {
@@ -170,6 +179,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [Cout rounded up to BLOCK_N]
     float* s_shift = s_scale + kMaxCout;
+    float4* epi_stage = reinterpret_cast<float4*>(s_shift + kMaxCout);            // [8 warps][32 rows][8 float4]
+    RowInfo* epi_rows = reinterpret_cast<RowInfo*>(epi_stage + kNumEpiWarps * 32 * 8);   // [8 warps][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const sb_conv_desc& d = p.d;
@@ -268,128 +279,162 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share each lane quarter and
-        // split the tile's columns in halves.
+        // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share each lane quarter and split the
+        // tile's columns in halves.  Per 32-column chunk: TMEM -> registers (one accumulator row per thread)
+        // -> scale/shift (one FFMA) -> XOR-swizzled per-warp staging tile in shared memory -> read back
+        // transposed so that every global access of the warp covers four full 128-byte rows.  The epilogue
+        // is instruction-issue bound (ncu: ~2 warp-instructions per output element before this rewrite), so
+        // row addressing is hoisted to once per tile and the residual / upsample paths are compile-time.
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;          // accumulator row == pixel inside the tile
+        const int ew = warp - 2;
+        const int half = ew >> 2;
         constexpr int kColsPerWarp = BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32;
         const int col_begin = half * kColsPerWarp;
         const bool has_cols = col_begin < BLOCK_N;
+        float4* stg = epi_stage + ew * (32 * 8);
+        RowInfo* ri = epi_rows + ew * 32;
         int acc = 0;
         uint32_t acc_phase = 0;
         float rh = 0.f, rw = 0.f;
-        if (d.up_src) {
+        if (HAS_UP) {
             rh = d.Ho > 1 ? __fdiv_rn((float)(d.UH - 1), (float)(d.Ho - 1)) : 0.f;
             rw = d.Wo > 1 ? __fdiv_rn((float)(d.UW - 1), (float)(d.Wo - 1)) : 0.f;
         }
+        const int rsub = lane >> 3, c4 = lane & 7;
+        const bool relu = d.relu != 0;
+        const int out_mode = d.out_mode;
+        const bool res_biased = d.res_biased != 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
-            int n_img, ho, wo;
-            bool valid;
-            if (p.patch) {
-                const int tw = mt % p.tiles_w;
-                const int t2 = mt / p.tiles_w;
-                ho = (t2 % p.tiles_h) * TH + row / TW;
-                wo = tw * TW + row % TW;
-                n_img = t2 / p.tiles_h;
-                valid = ho < d.Ho && wo < d.Wo;
-            } else {
-                const long long m = (long long)mt * BLOCK_M + row;
-                valid = m < p.M;
-                const long long mm = valid ? m : 0;
-                wo = (int)(mm % d.Wo);
-                const long long t2 = mm / d.Wo;
-                ho = (int)(t2 % d.Ho);
-                n_img = (int)(t2 / d.Ho);
+            {   // this lane describes accumulator row q*32+lane of the tile
+                const int row = q * 32 + lane;
+                int n_img, ho, wo;
+                bool valid;
+                if (p.patch) {
+                    const int tw = mt % p.tiles_w;
+                    const int t2 = mt / p.tiles_w;
+                    ho = (t2 % p.tiles_h) * TH + row / TW;
+                    wo = tw * TW + row % TW;
+                    n_img = t2 / p.tiles_h;
+                    valid = ho < d.Ho && wo < d.Wo;
+                } else {
+                    const long long m = (long long)mt * BLOCK_M + row;
+                    valid = m < p.M;
+                    const unsigned mm = valid ? (unsigned)m : 0u;      // M < 2^31 (checked on the host)
+                    const unsigned hw = (unsigned)(d.Ho * d.Wo);
+                    n_img = (int)(mm / hw);
+                    const unsigned rem = mm - (unsigned)n_img * hw;
+                    ho = (int)(rem / (unsigned)d.Wo);
+                    wo = (int)(rem - (unsigned)ho * (unsigned)d.Wo);
+                }
+                RowInfo inf;
+                inf.out_off = (long long)n_img * d.out_n_stride + (long long)ho * d.out_h_stride +
+                              (long long)wo * d.out_w_stride + d.out_coff;
+                inf.res_off = ((long long)(n_img * d.Ho + ho) * d.Wo + wo) * d.res_ld;
+                inf.flags = valid ? 1 : 0;
+                inf.up_off = 0; inf.ly1 = 0.f; inf.lx1 = 0.f;
+                if (HAS_UP) {
+                    const float sy = __fmul_rn(rh, (float)ho), sx = __fmul_rn(rw, (float)wo);
+                    const int y1 = (int)sy, x1 = (int)sx;
+                    if (y1 < d.UH - 1) inf.flags |= 2;
+                    if (x1 < d.UW - 1) inf.flags |= 4;
+                    inf.ly1 = sy - (float)y1;
+                    inf.lx1 = sx - (float)x1;
+                    inf.up_off = (((long long)n_img * d.UH + y1) * d.UW + x1) * d.Cout;
+                }
+                __syncwarp();
+                ri[lane] = inf;
+                __syncwarp();
             }
-            float* orow = d.out + (long long)n_img * d.out_n_stride + (long long)ho * d.out_h_stride +
-                          (long long)wo * d.out_w_stride + d.out_coff;
-            const float* rrow = d.residual
-                                    ? d.residual + ((long long)(n_img * d.Ho + ho) * d.Wo + wo) * d.res_ld
-                                    : nullptr;
-            const float *u00 = nullptr, *u01 = nullptr, *u10 = nullptr, *u11 = nullptr;
-            float ly0 = 0.f, ly1 = 0.f, lx0 = 0.f, lx1 = 0.f;
-            if (d.up_src) {
-                const float sy = __fmul_rn(rh, (float)ho), sx = __fmul_rn(rw, (float)wo);
-                const int y1 = (int)sy, x1 = (int)sx;
-                const int yp = y1 < d.UH - 1 ? 1 : 0, xp = x1 < d.UW - 1 ? 1 : 0;
-                ly1 = sy - (float)y1; ly0 = 1.f - ly1; lx1 = sx - (float)x1; lx0 = 1.f - lx1;
-                u00 = d.up_src + (((long long)n_img * d.UH + y1) * d.UW + x1) * d.Cout;
-                u01 = u00 + (long long)xp * d.Cout;
-                u10 = u00 + (long long)yp * d.UW * d.Cout;
-                u11 = u10 + (long long)xp * d.Cout;
+            // rows this lane touches in the coalesced domain: 4*i + rsub, i = 0..7
+            float* optr[8];
+            const float* rptr[8];
+            unsigned vmask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const RowInfo& inf = ri[4 * i + rsub];
+                optr[i] = d.out + inf.out_off + 4 * c4;
+                rptr[i] = HAS_RES ? d.residual + inf.res_off + 4 * c4 : nullptr;
+                vmask |= (unsigned)(inf.flags & 1) << i;
+            }
+            // residual rows are fetched into registers two chunks ahead -- the first two before the tile's
+            // accumulator is even complete, so the HBM latency hides behind the MMA main loop
+            constexpr int kChunks = kColsPerWarp / 32;
+            float4 r4[2][8];
+            const int cb0 = nt * BLOCK_N + col_begin;
+            auto load_res = [&](int buf, int k) {
+                const int cbase = cb0 + 32 * k;
+                const unsigned live = (cbase + 4 * c4 < d.Cout) ? vmask : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    r4[buf][i] = ((live >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(rptr[i] + cbase))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            if (HAS_RES && has_cols) {
+                load_res(0, 0);
+                if (kChunks > 1) load_res(1, 1);
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (has_cols) {
-#pragma unroll 1
-                for (int cc = col_begin; cc < col_begin + kColsPerWarp; cc += 32) {
+#pragma unroll
+                for (int k = 0; k < kChunks; ++k) {
+                    const int cc = col_begin + 32 * k;
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc), v);
                     const int cbase = nt * BLOCK_N + cc;
-                    const bool chunk_live = valid && cbase < d.Cout;
-                    const bool full = cbase + 31 < d.Cout;
-                    // issue the residual loads before waiting on TMEM
-                    float4 r4[8];
-                    if (chunk_live && rrow && full) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(rrow + cbase + 4 * j);
-                    }
+                    const unsigned live = (cbase + 4 * c4 < d.Cout) ? vmask : 0u;
                     tmem_ld_wait();
-                    if (chunk_live && full) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c = cbase + 4 * j;
-                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
-                            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
-                            float o[4];
-                            o[0] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 0]), sc.x), sh.x);
-                            o[1] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 1]), sc.y), sh.y);
-                            o[2] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 2]), sc.z), sh.z);
-                            o[3] = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * j + 3]), sc.w), sh.w);
-                            if (rrow) {
-                                float4 r = r4[j];
-                                if (d.res_biased) {
-                                    r.x = sb_unbias_tf32(r.x); r.y = sb_unbias_tf32(r.y);
-                                    r.z = sb_unbias_tf32(r.z); r.w = sb_unbias_tf32(r.w);
-                                }
-                                o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
-                            }
-                            if (u00) {
-                                const float4 a = *reinterpret_cast<const float4*>(u00 + c);
-                                const float4 b = *reinterpret_cast<const float4*>(u01 + c);
-                                const float4 g = *reinterpret_cast<const float4*>(u10 + c);
-                                const float4 h = *reinterpret_cast<const float4*>(u11 + c);
-                                o[0] += ly0 * (lx0 * a.x + lx1 * b.x) + ly1 * (lx0 * g.x + lx1 * h.x);
-                                o[1] += ly0 * (lx0 * a.y + lx1 * b.y) + ly1 * (lx0 * g.y + lx1 * h.y);
-                                o[2] += ly0 * (lx0 * a.z + lx1 * b.z) + ly1 * (lx0 * g.z + lx1 * h.z);
-                                o[3] += ly0 * (lx0 * a.w + lx1 * b.w) + ly1 * (lx0 * g.w + lx1 * h.w);
-                            }
-                            if (d.relu) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-                            }
-                            if (d.out_mode) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) o[e] = sb_store_mode(o[e], d.out_mode);
-                            }
-                            *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
-                        }
-                    } else if (chunk_live) {
-                        // ragged tail of the channel range (Cout not a multiple of 32): scalar path
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int c = cbase + j;
-                            if (c >= d.Cout) continue;
-                            float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j]), s_scale[c]), s_shift[c]);
-                            if (rrow) x += d.res_biased ? sb_unbias_tf32(rrow[c]) : rrow[c];
-                            if (u00)
-                                x += ly0 * (lx0 * u00[c] + lx1 * u01[c]) + ly1 * (lx0 * u10[c] + lx1 * u11[c]);
-                            if (d.relu) x = fmaxf(x, 0.f);
-                            orow[c] = sb_store_mode(x, d.out_mode);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + cbase + 4 * j);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + cbase + 4 * j);
+                        float4 o;
+                        o.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                        o.y = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                        o.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                        o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+                        stg[lane * 8 + (j ^ (lane & 7))] = o;
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + rsub;
+                        float4 x = stg[r * 8 + (c4 ^ (r & 7))];
+                        if (!((live >> i) & 1u)) continue;
+                        if (HAS_RES) {
+                            float4 rr = r4[k & 1][i];
+                            if (res_biased) {
+                                rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
+                                rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
+                            }
+                            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                        }
+                        if (HAS_UP) {
+                            const RowInfo inf = ri[r];
+                            const float* u00 = d.up_src + inf.up_off + cbase + 4 * c4;
+                            const long long dx = (inf.flags & 4) ? d.Cout : 0;
+                            const long long dy = (inf.flags & 2) ? (long long)d.UW * d.Cout : 0;
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(u00));
+                            const float4 bq = __ldg(reinterpret_cast<const float4*>(u00 + dx));
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(u00 + dy));
+                            const float4 h = __ldg(reinterpret_cast<const float4*>(u00 + dy + dx));
+                            const float ly1 = inf.ly1, ly0 = 1.f - ly1, lx1 = inf.lx1, lx0 = 1.f - lx1;
+                            x.x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
+                            x.y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
+                            x.z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
+                            x.w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
+                        }
+                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (out_mode == 1) {
+                            x.x = sb_round_tf32(x.x); x.y = sb_round_tf32(x.y); x.z = sb_round_tf32(x.z); x.w = sb_round_tf32(x.w);
+                        } else if (out_mode == 2) {
+                            x.x = sb_bias_tf32(x.x); x.y = sb_bias_tf32(x.y); x.z = sb_bias_tf32(x.z); x.w = sb_bias_tf32(x.w);
+                        }
+                        *reinterpret_cast<float4*>(optr[i] + cbase) = x;
+                    }
+                    __syncwarp();
+                    if (HAS_RES && k + 2 < kChunks) load_res(k & 1, k + 2);
                 }
             }
             tc_fence_before();
@@ -448,12 +493,13 @@ int pick_block_n(int cout, long long m_tiles, int num_sms) {
     return c256 <= c128 ? 256 : 128;
 }
 
-template <int BN, int ST>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4;
+template <int BN, int ST, bool RES, bool UP>
+int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    static_assert((size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem <= 227 * 1024, "smem budget");
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -466,10 +512,17 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    conv_tc_kernel<BN, ST><<<grid, kNumThreads, smem, st>>>(ma, mb, p);
+    conv_tc_kernel<BN, ST, RES, UP><<<grid, kNumThreads, smem, st>>>(ma, mb, p);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;
+}
+
+template <int BN, int ST>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    const bool res = p.d.residual != nullptr, up = p.d.up_src != nullptr;
+    if (up) return launch_t<BN, ST, false, true>(ma, mb, p, st);   // residual + upsample never co-occur (supported())
+    return res ? launch_t<BN, ST, true, false>(ma, mb, p, st) : launch_t<BN, ST, false, false>(ma, mb, p, st);
 }
 
 }  // namespace
@@ -480,7 +533,8 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
     const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0;
     const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1;
     if (!k1 && !k3) return 0;
-    if (d->Cout > kMaxCout) return 0;
+    if (d->Cout > kMaxCout || (d->Cout & 3)) return 0;
+    if (d->residual && d->up_src) return 0;
     if ((reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->wgt) & 15) ||
         (reinterpret_cast<uintptr_t>(d->out) & 15))
         return 0;
@@ -488,6 +542,7 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
     if (d->residual && ((d->res_ld & 3) || (reinterpret_cast<uintptr_t>(d->residual) & 15))) return 0;
     if (d->up_src && ((d->Cout & 3) || (reinterpret_cast<uintptr_t>(d->up_src) & 15))) return 0;
     if (d->Ho != d->H || d->Wo != d->W) return 0;
+    if ((long long)d->N * d->Ho * d->Wo >= 0x7fffffffLL) return 0;
     return 1;
 }
 
@@ -511,6 +566,7 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         if (sms <= 0) sms = 148;
     }
     int BN = pick_block_n(d->Cout, p.num_m_tiles, sms);
+    if (d->residual && BN == 256) BN = 128;   // residual layers are HBM-bound; the 256-wide residual epilogue spills
     if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256) BN = v; }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
     CUtensorMap ma, mb;
@@ -535,9 +591,9 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     }
     cudaStream_t st = sb_cs(stream);
     switch (BN) {
-        case 32: return launch<32, 8>(ma, mb, p, st);
-        case 64: return launch<64, 8>(ma, mb, p, st);
-        case 256: return launch<256, 4>(ma, mb, p, st);
-        default: return launch<128, 5>(ma, mb, p, st);
+        case 32: return launch<32, 6>(ma, mb, p, st);
+        case 64: return launch<64, 6>(ma, mb, p, st);
+        case 256: return launch<256, 3>(ma, mb, p, st);
+        default: return launch<128, 4>(ma, mb, p, st);
     }
 }

@@ -134,8 +134,10 @@ def test_conv_tc_tf32(case):
     if N * H * W * Co < 4e6:
         res = torch.randn(N, Co, H, W, generator=g)
         up = torch.randn(N, Co, (H + 1) // 2, (W + 1) // 2, generator=g)
-        y = run_conv(x, w, "tc", 1, p, None, sh, residual=res, up_src=up)
-        assert rel_err(y, ref_conv(x, w, 1, p, None, sh, residual=res, up_src=up)) < 1e-3
+        y = run_conv(x, w, "tc", 1, p, None, sh, residual=res)
+        assert rel_err(y, ref_conv(x, w, 1, p, None, sh, residual=res)) < 1e-3
+        y = run_conv(x, w, "tc", 1, p, None, sh, up_src=up, relu=True)
+        assert rel_err(y, ref_conv(x, w, 1, p, None, sh, up_src=up, relu=True)) < 1e-3
 
 
 def test_conv_tc_strided_outputs():
