@@ -96,7 +96,7 @@ class Pipeline(object):
         self.ops, self.dev = ops, device
         self.eng = engine.StereoRCNNEngine(make_state_dict(3), device)
         self.info = torch.tensor([[H_NET, W_NET, SCALE]], dtype=torch.float32, device=device)
-        self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "1") != "0" else None
+        self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "0") != "0" else None
 
     def step(self, iml, imr, calib4, rois3d):
         ops = self.ops

@@ -211,6 +211,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch,
+    // scale/shift staging -- weights only) overlapped the previous kernel's tail.  Let the next kernel start
+    // its own prologue as soon as our CTAs retire, then wait for the producers of our activations.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -512,8 +517,20 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    conv_tc_kernel<BN, ST, RES, UP><<<grid, kNumThreads, smem, st>>>(ma, mb, p);
+    static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, ST, RES, UP>, ma, mb, p);
     SB_LAUNCHED();
+    if (le != cudaSuccess) return (int)le;
     SB_CHECK_LAUNCH();
     return SB_OK;
 }

@@ -236,7 +236,7 @@ __device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, co
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 dense_align_kernel(const float4* __restrict__ upL, const float4* __restrict__ upR, Consts k,
                    const float* __restrict__ box_left, const float* __restrict__ keypoints,
                    const float* __restrict__ poses, int D, float* __restrict__ status,
@@ -350,7 +350,7 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     upsample2x_kernel<<<ug, 256, 0, st>>>(im_left, im_right, H, W, upL, upR);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
-    dense_align_kernel<<<D, 512, 0, st>>>(upL, upR, k, box_left, keypoints, poses, D, status, best_dis, dis_ws, flags);
+    dense_align_kernel<<<D, 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, D, status, best_dis, dis_ws, flags);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;
