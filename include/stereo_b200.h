@@ -141,7 +141,7 @@ int sb_conv2d_tc_supported(const sb_conv_desc* d);
 /* stem: NCHW image -> conv7x7/2 + frozen BN + ReLU -> NHWC (resnet.py:111-113) */
 int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[64][7][7][3]*/,
                  const float* scale, const float* shift, float* out_nhwc, int out_mode, sb_stream_t stream);
-/* stem as a tensor-core GEMM: patch matrix [N*Ho*Wo][160] (k = (r*7+s)*3+ci, zero padded from 147) that
+/* stem as a tensor-core GEMM: patch matrix [N*Ho*Wo][160] (k = ci*49+r*7+s, zero padded from 147) that
  * sb_conv2d_tc then multiplies with the [64][160] stem weights (1x1 conv, Cin = 160)              */
 int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream);
 /* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
@@ -152,7 +152,7 @@ int sb_subsample2(const float* in, int N, int H, int W, int C, float* out, sb_st
  * -> softmax over 4G / G / G (stereo_rcnn.py:262-271)                                    */
 int sb_kpts_tail(const float* x, int R, int G, int C, const float* w /*[6][C]*/, const float* b /*[6]*/,
                  float* kpts_prob /*[R,4G]*/, float* left_prob /*[R,G]*/, float* right_prob /*[R,G]*/,
-                 float* kpts_pred_all /*[R,6,G] or NULL*/, sb_stream_t stream);
+                 float* kpts_pred_all /*[R,6,G], required*/, sb_stream_t stream);
 /* box-head tail: fc7 [R,K] -> cls softmax [R,nc], bbox [R,6nc], dim_orien [R,5nc] */
 int sb_box_tail(const float* fc7, int R, int K, int n_classes,
                 const float* w_cls, const float* b_cls, const float* w_box, const float* b_box,

@@ -96,6 +96,27 @@ __device__ __forceinline__ float sb_store_mode(float x, int mode) {
     return mode == 1 ? sb_round_tf32(x) : (mode == 2 ? sb_bias_tf32(x) : x);
 }
 
+// sb_iou(a,b) > thresh, bit-identical in outcome, without the IEEE division for the common cases:
+// disjoint boxes have IoU == +0 (never > a non-negative thresh), and when inter and thresh*union differ by
+// more than 1e-4 relative the rounded quotient cannot land on the other side of thresh.
+__device__ __forceinline__ bool sb_iou_gt(const float4 a, const float4 b, float thresh) {
+    float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.0f), 0.f);
+    float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.0f), 0.f);
+    float interS = __fmul_rn(width, height);
+    if (interS == 0.f && thresh >= 0.f) return false;
+    float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+    float Sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+    float uni = __fsub_rn(__fadd_rn(Sa, Sb), interS);
+    float t = thresh * uni;
+    if (uni > 0.f && thresh > 0.f && isfinite(t)) {
+        if (interS > t * 1.0001f) return true;
+        if (interS < t * 0.9999f) return false;
+    }
+    return __fdiv_rn(interS, uni) > thresh;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

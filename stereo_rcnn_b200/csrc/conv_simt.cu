@@ -240,7 +240,8 @@ stem_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo,
 }
 
 // stem im2col: NCHW image -> rows of the 7x7/2 pad-3 patch matrix [M = N*Ho*Wo][160] with
-// k = (r*7+s)*3 + ci for k < 147 and zero padding up to 160 (a multiple of the 32-wide K tile of
+// k = ci*49 + r*7 + s (the reference's own [Cout][Cin][kh][kw] weight order: 4 consecutive k are
+// 4 consecutive input pixels of one row, i.e. one or two 32-byte sectors) for k < 147, zero up to 160 (a multiple of the 32-wide K tile of
 // the tcgen05 kernel).  One thread = one float4 (4 consecutive k) of one output pixel.
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo, float4* __restrict__ out) {
@@ -259,7 +260,7 @@ stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, in
         const int k = g * 4 + j;
         float x = 0.f;
         if (k < 147) {
-            const int tap = k / 3, ci = k - tap * 3;
+            const int ci = k / 49, tap = k - ci * 49;
             const int r = tap / 7, s2 = tap - r * 7;
             const int hi = ho * 2 - 3 + r, wi = wo * 2 - 3 + s2;
             if (hi >= 0 && hi < H && wi >= 0 && wi < W)

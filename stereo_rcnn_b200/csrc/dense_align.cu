@@ -8,13 +8,14 @@
 // Here:
 //   K1 upsample2x_kernel : both images, F.upsample(x2, bilinear, align_corners=True) written
 //      once as pixel-interleaved float4 (c0,c1,c2,0) so that a bilinear tap is one 128-bit load.
-//   K2 dense_align_kernel: one CTA per RoI.  Thread 0 builds the 3D box (corners, the three
-//      visible planes by the nearest-vertex rule) in registers/smem; every thread then owns
-//      lattice pixels (row-major, stride 256), runs the ray/plane/in-box test, samples the left
-//      image once and accumulates the SAD for all 50 (then 20) depth hypotheses in registers,
-//      warp-shuffle + smem reduction, in-kernel argmin.  The last CTA to finish applies the
-//      reference's "no valid pixel anywhere -> return dis_init" early-out.
-// Nothing but the two upsampled images (2 x 76 MB) and D x 2 outputs touches HBM.
+//   K2/K3 dense_stage_kernel<0|1>: grid (RoI, lattice slice).  Thread 0 builds the 3D box (corners, the
+//      three visible planes by the nearest-vertex rule); every thread owns lattice pixels (row-major,
+//      strided), runs the ray/plane/in-box test, samples the left image once and accumulates the SAD of all
+//      50 (coarse) or 20 (fine) depth hypotheses in registers; warp-shuffle + smem reduction to one partial
+//      row per CTA.  The fine stage re-derives the coarse argmin from the partial rows (fixed slice order).
+//   K4 dense_final_kernel: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere ->
+//      return dis_init" early-out.
+// Nothing but the two upsampled images (2 x 76 MB), a few KB of partial sums and D x 2 outputs touches HBM.
 //
 // Arithmetic mirrors oracle/csrc/oracle_ops.c (which is pinned to the reference's Python):
 // every fp32 step is an explicit _rn intrinsic in the reference's evaluation order.
@@ -188,17 +189,20 @@ __device__ __forceinline__ float3 grid_sample(const float4* __restrict__ im, int
     return v;
 }
 
+// One stage of the depth search for one (RoI, lattice slice).  Every thread owns lattice pixels
+// q = slice*blockDim + tid (+ nslices*blockDim ...), keeps the SAD of all NH hypotheses in registers and the
+// CTA writes one partial row [NH costs, valid-pixel count] to `part`.
 template <int NH>
 __device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, const float4* __restrict__ upL,
                                             const float4* __restrict__ upR, const float* __restrict__ rdis,
-                                            float* __restrict__ red /*[8][NH+1]*/, float* __restrict__ cost_out,
-                                            int* npix_out) {
+                                            float* __restrict__ red /*[8][NH+1]*/, int slice, int nslices,
+                                            float* __restrict__ part /*[NH+1] global*/) {
     float acc[NH];
 #pragma unroll
     for (int h = 0; h < NH; ++h) acc[h] = 0.f;
     int cnt = 0;
     const int total = g.nu * g.nv;
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    for (int q = slice * blockDim.x + threadIdx.x; q < total; q += nslices * blockDim.x) {
         const int a = q / g.nu, b = q - a * g.nu;
         const float u = (float)(g.u0 + b * g.su), v = (float)(g.v0 + a * g.sv);
         float dz;
@@ -230,84 +234,102 @@ __device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, co
     if (threadIdx.x <= NH) {
         float s = 0.f;
         for (int w = 0; w < nw; ++w) s += red[w * (NH + 1) + threadIdx.x];
-        if (threadIdx.x < NH) cost_out[threadIdx.x] = s;
-        else *npix_out = (int)s;
+        part[threadIdx.x] = s;
     }
-    __syncthreads();
 }
 
+// coarse depths (dense_align.py:280-285) and the argmin over the slices' partial sums (fixed slice order)
+__device__ __forceinline__ float coarse_depth(float z0, int h) {
+    float d = __fadd_rn(__fsub_rn(z0, 12.5f), (float)(0.5 * h));
+    return d < 1.5f ? 1.5f : d;
+}
+__device__ __forceinline__ int argmin_partials(const float* __restrict__ part, int nslices, int nh, int row,
+                                               float* npix) {
+    int bi = 0;
+    float bc = 0.f;
+    for (int h = 0; h < nh; ++h) {
+        float c = 0.f;
+        for (int s = 0; s < nslices; ++s) c += __ldcg(part + (size_t)s * row + h);
+        if (h == 0 || c < bc) { bc = c; bi = h; }
+    }
+    if (npix) {
+        float c = 0.f;
+        for (int s = 0; s < nslices; ++s) c += __ldcg(part + (size_t)s * row + nh);
+        *npix = c;
+    }
+    return bi;
+}
+
+// grid (D, S): S lattice slices per RoI so that a few dozen RoIs still fill the machine
+template <int STAGE>
 __global__ void __launch_bounds__(256)
-dense_align_kernel(const float4* __restrict__ upL, const float4* __restrict__ upR, Consts k,
+dense_stage_kernel(const float4* __restrict__ upL, const float4* __restrict__ upR, Consts k,
                    const float* __restrict__ box_left, const float* __restrict__ keypoints,
-                   const float* __restrict__ poses, int D, float* __restrict__ status,
-                   float* __restrict__ best_dis, float* __restrict__ dis_init_ws, int* __restrict__ flags) {
+                   const float* __restrict__ poses, float* __restrict__ part0 /*[D][S][51]*/,
+                   float* __restrict__ part1 /*[D][S][21]*/) {
     __shared__ RoiCtx g;
-    __shared__ float rdis[50], depth[50], cost[50];
-    __shared__ float red[16 * 51];
-    __shared__ int npix;
+    __shared__ float rdis[50];
+    __shared__ float red[8 * 51];
     __shared__ float best_depth;
-    __shared__ int is_last;
-    const int i = blockIdx.x;
-    if (threadIdx.x == 0) setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
+    const int i = blockIdx.x, S = gridDim.y;
+    if (threadIdx.x == 0) {
+        setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
+        if (STAGE == 1) best_depth = coarse_depth(g.z0, argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, nullptr));
+    }
     __syncthreads();
-    // coarse: depth_i = (1/dis_init*f*bl - 12.5) + 0.5 i, clamped at 1.5 (dense_align.py:280-285)
-    if (threadIdx.x < 50) {
-        float d = __fadd_rn(__fsub_rn(g.z0, 12.5f), (float)(0.5 * threadIdx.x));
-        if (d < 1.5f) d = 1.5f;
-        depth[threadIdx.x] = d;
+    constexpr int NH = STAGE == 0 ? 50 : 20;
+    if (threadIdx.x < NH) {
+        // fine: depth_j = (best - 0.5) + 0.05 j (dense_align.py:290-294)
+        const float d = STAGE == 0 ? coarse_depth(g.z0, threadIdx.x)
+                                   : __fadd_rn(__fsub_rn(best_depth, 0.5f), (float)(0.05 * threadIdx.x));
         rdis[threadIdx.x] = __fdiv_rn(1.0f, __fmul_rn(__fdiv_rn(1.0f, d), k.fb32));
     }
     __syncthreads();
-    stage_costs<50>(g, k, upL, upR, rdis, red, cost, &npix);
-    if (threadIdx.x == 0) {
-        int bi = 0;
-        for (int h = 1; h < 50; ++h) if (cost[h] < cost[bi]) bi = h;
-        best_depth = depth[bi];
-    }
+    float* part = STAGE == 0 ? part0 + ((size_t)i * S + blockIdx.y) * 51 : part1 + ((size_t)i * S + blockIdx.y) * 21;
+    stage_costs<NH>(g, k, upL, upR, rdis, red, blockIdx.y, S, part);
+}
+
+// one CTA: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere -> dis_init" early-out
+__global__ void __launch_bounds__(256)
+dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __restrict__ part0,
+                   const float* __restrict__ part1, int D, int S, float* __restrict__ status,
+                   float* __restrict__ best_dis) {
+    __shared__ int any_valid;
+    if (threadIdx.x == 0) any_valid = 0;
     __syncthreads();
-    // fine: depth_j = (best - 0.5) + 0.05 j (dense_align.py:290-294)
-    if (threadIdx.x < 20) {
-        float d = __fadd_rn(__fsub_rn(best_depth, 0.5f), (float)(0.05 * threadIdx.x));
-        depth[threadIdx.x] = d;
-        rdis[threadIdx.x] = __fdiv_rn(1.0f, __fmul_rn(__fdiv_rn(1.0f, d), k.fb32));
-    }
-    __syncthreads();
-    int npix2;
-    stage_costs<20>(g, k, upL, upR, rdis, red, cost, &npix);
-    (void)npix2;
-    if (threadIdx.x == 0) {
-        int bi = 0;
-        for (int h = 1; h < 20; ++h) if (cost[h] < cost[bi]) bi = h;
-        const float bd = depth[bi];
-        status[i] = npix > 0 ? 1.f : 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float dis_init = __fdiv_rn(k.fb32, poses[7 * i + 2]);
+        const float z0 = __fmul_rn(__fmul_rn(__fdiv_rn(1.0f, dis_init), k.f32), k.bl32);
+        float npix;
+        const float bd0 = coarse_depth(z0, argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, &npix));
+        const int bj = argmin_partials(part1 + (size_t)i * S * 21, S, 20, 21, nullptr);
+        const float bd = __fadd_rn(__fsub_rn(bd0, 0.5f), (float)(0.05 * bj));
+        status[i] = npix > 0.f ? 1.f : 0.f;
         best_dis[i] = __fadd_rn(__fdiv_rn(k.fb32, __fmul_rn(bd, k.s2f)), 0.5f);
-        dis_init_ws[i] = g.dis_init;
-        if (npix > 0) atomicOr(&flags[0], 1);
-        __threadfence();
-        is_last = (atomicAdd(&flags[1], 1) == D - 1);
+        if (npix > 0.f) any_valid = 1;
     }
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        if (atomicOr(&flags[0], 0) == 0) {   // dense_align.py:272-273: nothing valid anywhere
-            for (int j = threadIdx.x; j < D; j += blockDim.x) {
-                status[j] = 0.f;
-                best_dis[j] = __ldcg(dis_init_ws + j);
-            }
+    if (!any_valid) {   // dense_align.py:272-273
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            status[i] = 0.f;
+            best_dis[i] = __fdiv_rn(k.fb32, poses[7 * i + 2]);
         }
     }
 }
 
-struct DaLayout { size_t upL, upR, dis, flags, total; };
+constexpr int kMaxSlices = 8;
+
+struct DaLayout { size_t upL, upR, part0, part1, total; };
 DaLayout da_layout(int H, int W, int D) {
     DaLayout l;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
     size_t px = (size_t)4 * H * W;
+    const size_t d = (size_t)(D > 0 ? D : 1);
     l.upL = take(px * sizeof(float4));
     l.upR = take(px * sizeof(float4));
-    l.dis = take((size_t)(D > 0 ? D : 1) * sizeof(float));
-    l.flags = take(2 * sizeof(int));
+    l.part0 = take(d * kMaxSlices * 51 * sizeof(float));
+    l.part1 = take(d * kMaxSlices * 21 * sizeof(float));
     l.total = off;
     return l;
 }
@@ -328,8 +350,8 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     cudaStream_t st = sb_cs(stream);
     float4* upL = (float4*)(ws + l.upL);
     float4* upR = (float4*)(ws + l.upR);
-    float* dis_ws = (float*)(ws + l.dis);
-    int* flags = (int*)(ws + l.flags);
+    float* part0 = (float*)(ws + l.part0);
+    float* part1 = (float*)(ws + l.part1);
     // dense_align.py:255-266 (python floats = doubles, cast to fp32 where they meet a tensor)
     const double s2 = scale * 2.0;
     const double fd = calib4[0] * s2;
@@ -345,12 +367,17 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     k.FW = 2 * W;
     k.fw2 = (float)(((double)k.FW - 1.0) / 2.0);
     k.fh2 = (float)(((double)k.FH - 1.0) / 2.0);
-    cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
     dim3 ug((k.FW + 255) / 256, k.FH, 2);
     upsample2x_kernel<<<ug, 256, 0, st>>>(im_left, im_right, H, W, upL, upR);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
-    dense_align_kernel<<<D, 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, D, status, best_dis, dis_ws, flags);
+    int S = 296 / D;                  // two waves of 148 SMs worth of CTAs
+    S = S < 1 ? 1 : (S > kMaxSlices ? kMaxSlices : S);
+    dense_stage_kernel<0><<<dim3(D, S), 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, part0, part1);
+    SB_LAUNCHED();
+    dense_stage_kernel<1><<<dim3(D, S), 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, part0, part1);
+    SB_LAUNCHED();
+    dense_final_kernel<<<1, 256, 0, st>>>(k, poses, part0, part1, D, S, status, best_dis);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

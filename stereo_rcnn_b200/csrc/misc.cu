@@ -62,23 +62,30 @@ subsample2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, in
     out[e] = __ldg(in + (((long long)n * H + 2 * ho) * W + 2 * wo) * C4 + c);
 }
 
-// keypoint tail (stereo_rcnn.py:262-271): x [R,G,G,C] -> sum over height -> 1x1 conv C->6
-// -> softmax(4G), softmax(G), softmax(G).  One CTA per RoI, one thread per channel.
+// keypoint tail (stereo_rcnn.py:262-271): x [R,G,G,C] -> sum over height -> 1x1 conv C->6 -> [R,6,G]
+// (kernel 1: grid (R, 4 column groups), one thread per channel: 4x the CTAs of a per-RoI mapping so that
+// the 241 MB read runs with enough loads in flight), then softmax(4G), softmax(G), softmax(G) (kernel 2).
 __global__ void __launch_bounds__(256)
-kpts_tail_kernel(const float* __restrict__ x, int G, int C, const float* __restrict__ w,
-                 const float* __restrict__ b, float* __restrict__ kpts_prob, float* __restrict__ left_prob,
-                 float* __restrict__ right_prob, float* __restrict__ pred_all) {
-    extern __shared__ float sm[];       // [8][6] partials + [6][G] logits
-    float* part = sm;
-    float* ka = sm + 48;
+kpts_colsum_kernel(const float* __restrict__ x, int G, int C, int cols_per_cta, const float* __restrict__ w,
+                   const float* __restrict__ b, float* __restrict__ pred_all) {
+    __shared__ float part[8 * 6];
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
     const float* xr = x + (size_t)r * G * G * C;
-    for (int col = 0; col < G; ++col) {
+    const int col0 = blockIdx.y * cols_per_cta, col1 = min(G, col0 + cols_per_cta);
+    for (int col = col0; col < col1; ++col) {
         float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int c = tid; c < C; c += blockDim.x) {
-            float s = 0.f;
-            for (int h = 0; h < G; ++h) s += __ldg(xr + ((size_t)h * G + col) * C + c);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int h = 0;
+            for (; h + 3 < G; h += 4) {
+                s0 += __ldg(xr + ((size_t)(h + 0) * G + col) * C + c);
+                s1 += __ldg(xr + ((size_t)(h + 1) * G + col) * C + c);
+                s2 += __ldg(xr + ((size_t)(h + 2) * G + col) * C + c);
+                s3 += __ldg(xr + ((size_t)(h + 3) * G + col) * C + c);
+            }
+            for (; h < G; ++h) s0 += __ldg(xr + ((size_t)h * G + col) * C + c);
+            const float s = (s0 + s1) + (s2 + s3);
 #pragma unroll
             for (int j = 0; j < 6; ++j) p[j] = fmaf(w[j * C + c], s, p[j]);
         }
@@ -91,26 +98,27 @@ kpts_tail_kernel(const float* __restrict__ x, int G, int C, const float* __restr
         if (tid < 6) {
             float s = 0.f;
             for (int q = 0; q < nw; ++q) s += part[q * 6 + tid];
-            ka[tid * G + col] = s + (float)G * b[tid];
+            pred_all[((size_t)r * 6 + tid) * G + col] = s + (float)G * b[tid];
         }
         __syncthreads();
     }
-    if (pred_all)
-        for (int e = tid; e < 6 * G; e += blockDim.x) pred_all[(size_t)r * 6 * G + e] = ka[e];
-    // three softmaxes: warp 0 -> kpts (4G), warp 1 -> left (G), warp 2 -> right (G)
-    if (warp < 3) {
-        const int n = warp == 0 ? 4 * G : G;
-        const float* src = warp == 0 ? ka : ka + (3 + warp) * G;
-        float* dst = warp == 0 ? kpts_prob + (size_t)r * 4 * G
-                               : (warp == 1 ? left_prob : right_prob) + (size_t)r * G;
-        float m = -INFINITY;
-        for (int e = lane; e < n; e += 32) m = fmaxf(m, src[e]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int e = lane; e < n; e += 32) s += expf(src[e] - m);
-        s = warp_sum(s);
-        for (int e = lane; e < n; e += 32) dst[e] = expf(src[e] - m) / s;
-    }
+}
+
+__global__ void __launch_bounds__(96)
+kpts_softmax_kernel(const float* __restrict__ pred_all, int G, float* __restrict__ kpts_prob,
+                    float* __restrict__ left_prob, float* __restrict__ right_prob) {
+    const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* ka = pred_all + (size_t)r * 6 * G;
+    const int n = warp == 0 ? 4 * G : G;
+    const float* src = warp == 0 ? ka : ka + (3 + warp) * G;
+    float* dst = warp == 0 ? kpts_prob + (size_t)r * 4 * G : (warp == 1 ? left_prob : right_prob) + (size_t)r * G;
+    float m = -INFINITY;
+    for (int e = lane; e < n; e += 32) m = fmaxf(m, src[e]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int e = lane; e < n; e += 32) s += expf(src[e] - m);
+    s = warp_sum(s);
+    for (int e = lane; e < n; e += 32) dst[e] = expf(src[e] - m) / s;
 }
 
 // box tail (stereo_rcnn.py:253-257): three linears on fc7 + softmax over classes
@@ -252,7 +260,7 @@ class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ box
             unsigned long long bits = 0;
             const int j0 = w * 64, j1 = min(n, j0 + 64);
             for (int j = max(j0, t + 1); j < j1; ++j)
-                if (sb_iou(cur, sbox[j]) > nms_thresh) bits |= 1ULL << (j - j0);
+                if (sb_iou_gt(cur, sbox[j], nms_thresh)) bits |= 1ULL << (j - j0);
             mask[t][w] = bits;
         }
     }
@@ -305,8 +313,12 @@ extern "C" int sb_subsample2(const float* in, int N, int H, int W, int C, float*
 extern "C" int sb_kpts_tail(const float* x, int R, int G, int C, const float* w, const float* b, float* kpts_prob,
                             float* left_prob, float* right_prob, float* kpts_pred_all, sb_stream_t stream) {
     if (R == 0) return SB_OK;
-    size_t smem = (48 + 6 * (size_t)G) * sizeof(float);
-    kpts_tail_kernel<<<R, 256, smem, sb_cs(stream)>>>(x, G, C, w, b, kpts_prob, left_prob, right_prob, kpts_pred_all);
+    if (!kpts_pred_all) return SB_EINVAL;     // [R,6,G] logits are also the staging buffer between the two kernels
+    const int groups = 4, cols = (G + groups - 1) / groups;
+    kpts_colsum_kernel<<<dim3(R, groups), 256, 0, sb_cs(stream)>>>(x, G, C, cols, w, b, kpts_pred_all);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    kpts_softmax_kernel<<<R, 96, 0, sb_cs(stream)>>>(kpts_pred_all, G, kpts_prob, left_prob, right_prob);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -47,7 +47,7 @@ nms_mask_kernel(const float* __restrict__ boxes0, const float* __restrict__ boxe
         unsigned long long bits = 0;
         const int start = (row == col) ? t + 1 : 0;
         for (int j = start; j < col_size; ++j)
-            if (sb_iou(cur, cbox[j]) > thresh) bits |= 1ULL << j;
+            if (sb_iou_gt(cur, cbox[j], thresh)) bits |= 1ULL << j;
         mask[(size_t)i * cb + col] = bits;
     }
 }

@@ -64,7 +64,7 @@ class StereoRCNNEngine(object):
         s, b = bn_fold("RCNN_layer0.1")
         self.stem = (_pack_conv(sd["RCNN_layer0.0.weight"]), s, b)
         wst = torch.zeros(64, 160, 1, 1, device=self.device)          # stem as a GEMM over the padded patch matrix
-        wst[:, :147, 0, 0] = self.stem[0].reshape(64, 147)
+        wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)      # (ci, r, s) order of sb_stem_im2col
         self.p["stem_gemm"] = PackedConv(wst, s, b, 0)
         for li, nb in enumerate(LAYERS):
             for bi in range(nb):

@@ -270,7 +270,7 @@ def kpts_tail(x, w, b, want_pred_all=False):
     kp = torch.empty(R, 4 * G, dtype=torch.float32, device=dev)
     lp = torch.empty(R, G, dtype=torch.float32, device=dev)
     rp = torch.empty(R, G, dtype=torch.float32, device=dev)
-    ka = torch.empty(R, 6, G, dtype=torch.float32, device=dev) if want_pred_all else None
+    ka = torch.empty(R, 6, G, dtype=torch.float32, device=dev)      # logits; also the staging between the 2 kernels
     check(L.sb_kpts_tail(ptr(x), R, G, C, ptr(w), ptr(b), ptr(kp), ptr(lp), ptr(rp), ptr(ka), stream_ptr()),
           "sb_kpts_tail")
     return kp, lp, rp, ka
