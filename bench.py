@@ -164,10 +164,37 @@ def run_ours(args):
             pipe.par.gather_records(rec, world, dist, out=gathered)
         return rec, dis
 
+    # end-to-end: the H2D copy of pair k+1 (pinned host -> staging buffer, copy stream) overlaps the compute of
+    # pair k; every step still moves its own 28.6 MB in and its record out inside the timed region
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [(torch.empty_like(iml), torch.empty_like(imr)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "primed": False}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            staging[slot][0].copy_(host_l, non_blocking=True)
+            staging[slot][1].copy_(host_r, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    for ev in freed:
+        ev.record()
+
     def step_e2e():
         if use_graph:
-            iml.copy_(host_l, non_blocking=True)
-            imr.copy_(host_r, non_blocking=True)
+            k = state["k"]
+            if not state["primed"]:
+                prefetch(k % 2)
+                state["primed"] = True
+            main = torch.cuda.current_stream()
+            main.wait_event(ready[k % 2])
+            iml.copy_(staging[k % 2][0], non_blocking=True)      # device-to-device into the graph's fixed inputs
+            imr.copy_(staging[k % 2][1], non_blocking=True)
+            freed[k % 2].record(main)
+            prefetch((k + 1) % 2)                                 # next pair's H2D runs under this pair's compute
+            state["k"] = k + 1
             rec, keep, nkeep, st, dis = runner()
         else:
             a = host_l.to(dev, non_blocking=True)
@@ -283,13 +310,13 @@ def conv_time_per_step(pipe, iml, imr):
 def _cpu_threads():
     n = os.cpu_count() or 1
     import torch.nn.functional as F
-    x, w = torch.randn(1, 64, 48, 64), torch.randn(64, 64, 3, 3)
+    x, w = torch.randn(2, 256, 38, 125), torch.randn(256, 256, 3, 3)     # a layer-3 sized conv (11 GFLOP)
     best, best_t = 1, None
-    for nt in sorted({1, n}):
+    for nt in sorted({1, max(1, n // 2), n}):
         torch.set_num_threads(nt)
         F.conv2d(x, w, padding=1)
         t = time.time()
-        for _ in range(3):
+        for _ in range(2):
             F.conv2d(x, w, padding=1)
         t = time.time() - t
         if best_t is None or t < best_t:
@@ -327,9 +354,10 @@ def pick_crop(threads):
     for _ in range(3):
         F.conv2d(x, w, padding=1)
     rate = 3 * 2 * 38 * 125 * 256 * 256 * 9 / (time.time() - t)        # FLOP/s
-    full = 2 * (TC_GMACS_PER_PAIR + 5.6) * 1e9 / rate
+    fixed = 2 * (16.7 + 223.9) * 1e9 / rate                            # RoI heads: 300 RoIs whatever the crop
+    scal = 2 * (TC_GMACS_PER_PAIR - 16.7 - 223.9 + 5.6) * 1e9 / rate   # trunk + FPN + RPN scale with the pixels
     for frac, wcrop in ((1.0, W_NET), (0.5, 993), (0.25, 497), (0.125, 248)):
-        if full * frac <= 8.0 or wcrop == 248:
+        if fixed + scal * frac <= 10.0 or wcrop == 248:
             return wcrop, frac
 
 

@@ -66,7 +66,8 @@ int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W,
 
 /* Fused PyramidRoI_Feat: level routing (Q14) + per-level scale (Q15) + tap lattice +
  * 2x2/stride-1 average, NHWC features, one launch for all levels.
- * feats[l]: N x H_l x W_l x C (l = P2..P5); out[r][ph][pw][out_coff + c], row pitch out_ld floats. */
+ * feats[l]: N x H_l x W_l x C (l = P2..P5); out[r][ph][pw][out_coff + c], row pitch out_ld elements;
+ * round_tf32: 0 = exact fp32, 1 = fp32 rounded to TF32, 2 = __half output (out is then a __half*). */
 int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* heights, const int* widths,
                               int C, float im_h, const float* rois, int R, int pooled,
                               float* out, int out_ld, int out_coff, int round_tf32, sb_stream_t stream);
@@ -131,6 +132,11 @@ typedef struct {
      *   res_biased: the residual tensor is stored pre-biased;  in_biased: the input is (SIMT kernel only) */
     int out_mode, res_biased, in_biased;
     long long out_n_stride, out_h_stride, out_w_stride;
+    /* fp16 operand mode of the tensor-core kernel (kind::f16, fp32 accumulate): in/wgt point to __half data
+     * (in_dtype 1, Cin % 64 == 0); out16, when non-NULL, receives an fp16 (round-to-nearest) twin of the
+     * output with the same element strides; out may be NULL when only the fp16 twin is wanted.          */
+    void* out16;
+    int in_dtype, reserved0;
 } sb_conv_desc;
 
 int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream);
@@ -144,13 +150,16 @@ int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[
 /* stem as a tensor-core GEMM: patch matrix [N*Ho*Wo][160] (k = ci*49+r*7+s, zero padded from 147) that
  * sb_conv2d_tc then multiplies with the [64][160] stem weights (1x1 conv, Cin = 160)              */
 int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream);
+/* fp16 variant: rows of 192 __half (147 taps zero padded to three 64-wide K-steps of kind::f16) */
+int sb_stem_im2col16(const float* im_nchw, int N, int H, int W, void* out_half, sb_stream_t stream);
 /* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
 int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
+int sb_maxpool3x3s2_ceil16(const void* in_half, int N, int H, int W, int C, void* out_half, sb_stream_t stream);
 /* x[:, ::2, ::2, :] (stride-2 1x1 convs of resnet.py:71 and P6 of stereo_rcnn.py:39) */
 int sb_subsample2(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
 /* keypoint tail: relu'd deconv output [R,G,G,C] -> sum over height -> 1x1 (C->6) -> [R,6,G]
  * -> softmax over 4G / G / G (stereo_rcnn.py:262-271)                                    */
-int sb_kpts_tail(const float* x, int R, int G, int C, const float* w /*[6][C]*/, const float* b /*[6]*/,
+int sb_kpts_tail(const void* x, int x_is_half, int R, int G, int C, const float* w /*[6][C]*/, const float* b /*[6]*/,
                  float* kpts_prob /*[R,4G]*/, float* left_prob /*[R,G]*/, float* right_prob /*[R,G]*/,
                  float* kpts_pred_all /*[R,6,G], required*/, sb_stream_t stream);
 /* box-head tail: fc7 [R,K] -> cls softmax [R,nc], bbox [R,6nc], dim_orien [R,5nc] */

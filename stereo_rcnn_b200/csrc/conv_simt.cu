@@ -10,6 +10,8 @@
 // Tile: 128 output pixels x 64 output channels per CTA, K chunks of 16 input channels of
 // one filter tap; 256 threads, 8x4 accumulators each; A/B staged through shared memory
 // with 128-bit global loads, register-prefetched one chunk ahead.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -271,7 +273,51 @@ stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, in
     out[e] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// fp16 variant for the kind::f16 GEMM: rows of 192 halves (147 taps, zero padded to 3 K-steps of 64);
+// one thread = 8 consecutive k (one 16-byte store)
+__global__ void __launch_bounds__(256)
+stem_im2col16_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo, uint4* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * 24;
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const int g = (int)(e % 24);
+    long long t = e / 24;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float* base = im + (long long)n * 3 * H * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = g * 8 + j;
+        float x = 0.f;
+        if (k < 147) {
+            const int ci = k / 49, tap = k - ci * 49;
+            const int r = tap / 7, s2 = tap - r * 7;
+            const int hi = ho * 2 - 3 + r, wi = wo * 2 - 3 + s2;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) x = __ldg(base + ((long long)ci * H + hi) * W + wi);
+        }
+        v[j] = x;
+    }
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+    out[e] = o;
+}
+
 }  // namespace
+
+extern "C" int sb_stem_im2col16(const float* im_nchw, int N, int H, int W, void* out_half, sb_stream_t stream) {
+    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    const long long total = (long long)N * Ho * Wo * 24;
+    if (total <= 0) return SB_EINVAL;
+    stem_im2col16_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, (uint4*)out_half);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
 
 extern "C" int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream) {
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;

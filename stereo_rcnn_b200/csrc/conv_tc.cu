@@ -24,6 +24,7 @@
 //     scale/shift or bias, residual add, FPN bilinear (align_corners) upsample-add, ReLU,
 //     strided / channel-offset stores (RPN L/R concat, deconv scatter).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -31,8 +32,8 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;   // fp32 elements = 128 bytes = one swizzle row
-constexpr int UMMA_K = 8;     // tf32
+constexpr int kRowBytes = 128;  // one swizzle row per pixel per K-step: 32 fp32 (kind::tf32, K=8 per MMA)
+                                // or 64 fp16 (kind::f16, K=16 per MMA); four MMAs per K-step either way
 constexpr int TW = 16, TH = 8;  // spatial patch of a 3x3 tile (TW*TH == BLOCK_M)
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
@@ -100,8 +101,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=TF32 (2<<7),
 // B=TF32 (2<<10), A/B K-major (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {
+    return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
@@ -110,6 +112,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
@@ -162,11 +173,12 @@ struct TcParams {
     long long M;
 };
 
-template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP>
+template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p) {
-    constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 4, kBBytes = BLOCK_N * BLOCK_K * 4;
+    constexpr uint32_t kABytes = BLOCK_M * kRowBytes, kBBytes = BLOCK_N * kRowBytes;
+    constexpr int BLOCK_K = IN16 ? 64 : 32;     // elements per K-step
     constexpr uint32_t kStageBytes = kABytes + kBBytes;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -254,7 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(BLOCK_N);
+        constexpr uint32_t idesc = make_idesc(BLOCK_N, IN16);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -270,9 +282,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    for (int k = 0; k < 4; ++k) {
                         // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in 16-byte units
-                        umma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        if (IN16) umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        else umma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty[stage]);                       // frees the smem slot when the MMAs retire
                     if (kb == p.num_k_blocks - 1) umma_commit(&tfull[acc]);  // accumulator complete
@@ -352,13 +365,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __syncwarp();
             }
             // rows this lane touches in the coalesced domain: 4*i + rsub, i = 0..7
-            float* optr[8];
+            long long ooff[8];
             const float* rptr[8];
             unsigned vmask = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const RowInfo& inf = ri[4 * i + rsub];
-                optr[i] = d.out + inf.out_off + 4 * c4;
+                ooff[i] = inf.out_off + 4 * c4;
                 rptr[i] = HAS_RES ? d.residual + inf.res_off + 4 * c4 : nullptr;
                 vmask |= (unsigned)(inf.flags & 1) << i;
             }
@@ -436,7 +449,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         } else if (out_mode == 2) {
                             x.x = sb_bias_tf32(x.x); x.y = sb_bias_tf32(x.y); x.z = sb_bias_tf32(x.z); x.w = sb_bias_tf32(x.w);
                         }
-                        *reinterpret_cast<float4*>(optr[i] + cbase) = x;
+                        if (d.out) *reinterpret_cast<float4*>(d.out + ooff[i] + cbase) = x;
+                        if (d.out16) {   // fp16 twin (round to nearest) for the next tensor-core consumer
+                            __half2 lo = __floats2half2_rn(out_mode == 2 ? sb_unbias_tf32(x.x) : x.x, out_mode == 2 ? sb_unbias_tf32(x.y) : x.y);
+                            __half2 hi = __floats2half2_rn(out_mode == 2 ? sb_unbias_tf32(x.z) : x.z, out_mode == 2 ? sb_unbias_tf32(x.w) : x.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + cbase) = pk;
+                        }
                     }
                     __syncwarp();
                     if (HAS_RES && k + 2 < kChunks) load_res(k & 1, k + 2);
@@ -476,11 +497,11 @@ EncodeTiledFn get_encode() {
 }
 
 bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box) {
+              const cuuint32_t* box, bool f16) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims,
                      strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -498,13 +519,13 @@ int pick_block_n(int cout, long long m_tiles, int num_sms) {
     return c256 <= c128 ? 256 : 128;
 }
 
-template <int BN, int ST, bool RES, bool UP>
+template <int BN, int ST, bool RES, bool UP, bool IN16>
 int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    static_assert((size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem <= 227 * 1024, "smem budget");
-    constexpr size_t smem = (size_t)ST * (BLOCK_M * BLOCK_K * 4 + BN * BLOCK_K * 4) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem;
+    static_assert((size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem <= 227 * 1024, "smem budget");
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -528,7 +549,7 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, ST, RES, UP>, ma, mb, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, ST, RES, UP, IN16>, ma, mb, p);
     SB_LAUNCHED();
     if (le != cudaSuccess) return (int)le;
     SB_CHECK_LAUNCH();
@@ -537,23 +558,30 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
 
 template <int BN, int ST>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    const bool res = p.d.residual != nullptr, up = p.d.up_src != nullptr;
-    if (up) return launch_t<BN, ST, false, true>(ma, mb, p, st);   // residual + upsample never co-occur (supported())
-    return res ? launch_t<BN, ST, true, false>(ma, mb, p, st) : launch_t<BN, ST, false, false>(ma, mb, p, st);
+    const bool res = p.d.residual != nullptr, up = p.d.up_src != nullptr;   // never both (supported())
+    if (p.d.in_dtype == 1) {
+        if (up) return launch_t<BN, ST, false, true, true>(ma, mb, p, st);
+        return res ? launch_t<BN, ST, true, false, true>(ma, mb, p, st) : launch_t<BN, ST, false, false, true>(ma, mb, p, st);
+    }
+    if (up) return launch_t<BN, ST, false, true, false>(ma, mb, p, st);
+    return res ? launch_t<BN, ST, true, false, false>(ma, mb, p, st) : launch_t<BN, ST, false, false, false>(ma, mb, p, st);
 }
 
 }  // namespace
 
 extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
-    if (!d || !d->in || !d->wgt || !d->out) return 0;
-    if (d->stride != 1 || d->Cin % BLOCK_K != 0 || d->in_ld % 4 != 0) return 0;
+    if (!d || !d->in || !d->wgt) return 0;
+    const int bk = d->in_dtype == 1 ? 64 : 32;
+    if (d->in_dtype != 0 && d->in_dtype != 1) return 0;
+    if (d->stride != 1 || d->Cin % bk != 0 || d->in_ld % (d->in_dtype == 1 ? 8 : 4) != 0) return 0;
+    if (!d->out && !d->out16) return 0;
     const bool k1 = d->kh == 1 && d->kw == 1 && d->pad == 0;
     const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1;
     if (!k1 && !k3) return 0;
     if (d->Cout > kMaxCout || (d->Cout & 3)) return 0;
     if (d->residual && d->up_src) return 0;
     if ((reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->wgt) & 15) ||
-        (reinterpret_cast<uintptr_t>(d->out) & 15))
+        (reinterpret_cast<uintptr_t>(d->out) & 15) || (reinterpret_cast<uintptr_t>(d->out16) & 7))
         return 0;
     if ((d->out_coff & 3) || (d->out_n_stride & 3) || (d->out_h_stride & 3) || (d->out_w_stride & 3)) return 0;
     if (d->residual && ((d->res_ld & 3) || (reinterpret_cast<uintptr_t>(d->residual) & 15))) return 0;
@@ -570,6 +598,9 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     p.patch = (d->kh == 3) ? 1 : 0;
     p.M = (long long)d->N * d->Ho * d->Wo;
     if (p.M == 0) return SB_OK;
+    const bool f16 = d->in_dtype == 1;
+    const int BLOCK_K = f16 ? 64 : 32;
+    const int esz = f16 ? 2 : 4;
     p.kblocks_per_tap = d->Cin / BLOCK_K;
     p.num_k_blocks = d->kh * d->kw * p.kblocks_per_tap;
     p.tiles_w = (d->W + TW - 1) / TW;
@@ -589,22 +620,22 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     CUtensorMap ma, mb;
     if (p.patch) {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-        cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * 4, (cuuint64_t)d->W * d->in_ld * 4,
-                                 (cuuint64_t)d->H * d->W * d->in_ld * 4};
-        cuuint32_t box[4] = {BLOCK_K, TW, TH, 1};
-        if (!make_map(&ma, d->in, 4, dims, strides, box)) return SB_EINVAL;
+        cuuint64_t strides[3] = {(cuuint64_t)d->in_ld * esz, (cuuint64_t)d->W * d->in_ld * esz,
+                                 (cuuint64_t)d->H * d->W * d->in_ld * esz};
+        cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, TW, TH, 1};
+        if (!make_map(&ma, d->in, 4, dims, strides, box, f16)) return SB_EINVAL;
     } else {
         cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)p.M};
-        cuuint64_t strides[1] = {(cuuint64_t)d->in_ld * 4};
-        cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
-        if (!make_map(&ma, d->in, 2, dims, strides, box)) return SB_EINVAL;
+        cuuint64_t strides[1] = {(cuuint64_t)d->in_ld * esz};
+        cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, BLOCK_M};
+        if (!make_map(&ma, d->in, 2, dims, strides, box, f16)) return SB_EINVAL;
     }
     {
         const cuuint64_t ktot = (cuuint64_t)d->kh * d->kw * d->Cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout};
-        cuuint64_t strides[1] = {ktot * 4};
-        cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)BN};
-        if (!make_map(&mb, d->wgt, 2, dims, strides, box)) return SB_EINVAL;
+        cuuint64_t strides[1] = {ktot * esz};
+        cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
+        if (!make_map(&mb, d->wgt, 2, dims, strides, box, f16)) return SB_EINVAL;
     }
     cudaStream_t st = sb_cs(stream);
     switch (BN) {

@@ -1,5 +1,7 @@
 // misc.cu -- small memory-bound layer ops of the Stereo R-CNN forward (sm_100a):
 // max-pool, stride-2 subsample, keypoint-head tail, box-head tail, test-time decode.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 unsigned long long g_sb_launches = 0;
@@ -48,6 +50,38 @@ maxpool_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int H
     out[e] = m;
 }
 
+// fp16 twin of maxpool_kernel: 8 channels (one 16-byte vector) per thread
+__global__ void __launch_bounds__(256)
+maxpool16_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8, int Ho, int Wo, uint4* __restrict__ out) {
+    const long long total = (long long)N * Ho * Wo * C8;
+    long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % C8);
+    long long t = e / C8;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
+    for (int r = 0; r < 3; ++r) {
+        const int hi = ho * 2 + r;
+        if (hi >= H) break;
+        for (int s = 0; s < 3; ++s) {
+            const int wi = wo * 2 + s;
+            if (wi >= W) break;
+            const uint4 v = __ldg(in + (((long long)n * H + hi) * W + wi) * C8 + c);
+            m0 = __hmax2(m0, *reinterpret_cast<const __half2*>(&v.x));
+            m1 = __hmax2(m1, *reinterpret_cast<const __half2*>(&v.y));
+            m2 = __hmax2(m2, *reinterpret_cast<const __half2*>(&v.z));
+            m3 = __hmax2(m3, *reinterpret_cast<const __half2*>(&v.w));
+        }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+    o.z = *reinterpret_cast<uint32_t*>(&m2); o.w = *reinterpret_cast<uint32_t*>(&m3);
+    out[e] = o;
+}
+
 __global__ void __launch_bounds__(256)
 subsample2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, int Ho, int Wo,
                   float4* __restrict__ out) {
@@ -65,13 +99,17 @@ subsample2_kernel(const float4* __restrict__ in, int N, int H, int W, int C4, in
 // keypoint tail (stereo_rcnn.py:262-271): x [R,G,G,C] -> sum over height -> 1x1 conv C->6 -> [R,6,G]
 // (kernel 1: grid (R, 4 column groups), one thread per channel: 4x the CTAs of a per-RoI mapping so that
 // the 241 MB read runs with enough loads in flight), then softmax(4G), softmax(G), softmax(G) (kernel 2).
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __half* p) { return __half2float(__ldg(p)); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-kpts_colsum_kernel(const float* __restrict__ x, int G, int C, int cols_per_cta, const float* __restrict__ w,
+kpts_colsum_kernel(const T* __restrict__ x, int G, int C, int cols_per_cta, const float* __restrict__ w,
                    const float* __restrict__ b, float* __restrict__ pred_all) {
     __shared__ float part[8 * 6];
     const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
-    const float* xr = x + (size_t)r * G * G * C;
+    const T* xr = x + (size_t)r * G * G * C;
     const int col0 = blockIdx.y * cols_per_cta, col1 = min(G, col0 + cols_per_cta);
     for (int col = col0; col < col1; ++col) {
         float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -79,12 +117,12 @@ kpts_colsum_kernel(const float* __restrict__ x, int G, int C, int cols_per_cta, 
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             int h = 0;
             for (; h + 3 < G; h += 4) {
-                s0 += __ldg(xr + ((size_t)(h + 0) * G + col) * C + c);
-                s1 += __ldg(xr + ((size_t)(h + 1) * G + col) * C + c);
-                s2 += __ldg(xr + ((size_t)(h + 2) * G + col) * C + c);
-                s3 += __ldg(xr + ((size_t)(h + 3) * G + col) * C + c);
+                s0 += ld_as_float(xr + ((size_t)(h + 0) * G + col) * C + c);
+                s1 += ld_as_float(xr + ((size_t)(h + 1) * G + col) * C + c);
+                s2 += ld_as_float(xr + ((size_t)(h + 2) * G + col) * C + c);
+                s3 += ld_as_float(xr + ((size_t)(h + 3) * G + col) * C + c);
             }
-            for (; h < G; ++h) s0 += __ldg(xr + ((size_t)h * G + col) * C + c);
+            for (; h < G; ++h) s0 += ld_as_float(xr + ((size_t)h * G + col) * C + c);
             const float s = (s0 + s1) + (s2 + s3);
 #pragma unroll
             for (int j = 0; j < 6; ++j) p[j] = fmaf(w[j * C + c], s, p[j]);
@@ -300,6 +338,17 @@ extern "C" int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C,
     return SB_OK;
 }
 
+extern "C" int sb_maxpool3x3s2_ceil16(const void* in, int N, int H, int W, int C, void* out, sb_stream_t stream) {
+    if (C & 7) return SB_EINVAL;
+    auto osz = [](int x) { int o = (x - 3 + 1) / 2 + 1; if ((o - 1) * 2 >= x) --o; return o; };
+    const int Ho = osz(H), Wo = osz(W);
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    maxpool16_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>((const uint4*)in, N, H, W, C / 8, Ho, Wo, (uint4*)out);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
 extern "C" int sb_subsample2(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream) {
     if (C & 3) return SB_EINVAL;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
@@ -310,12 +359,16 @@ extern "C" int sb_subsample2(const float* in, int N, int H, int W, int C, float*
     return SB_OK;
 }
 
-extern "C" int sb_kpts_tail(const float* x, int R, int G, int C, const float* w, const float* b, float* kpts_prob,
-                            float* left_prob, float* right_prob, float* kpts_pred_all, sb_stream_t stream) {
+extern "C" int sb_kpts_tail(const void* x, int x_is_half, int R, int G, int C, const float* w, const float* b,
+                            float* kpts_prob, float* left_prob, float* right_prob, float* kpts_pred_all,
+                            sb_stream_t stream) {
     if (R == 0) return SB_OK;
     if (!kpts_pred_all) return SB_EINVAL;     // [R,6,G] logits are also the staging buffer between the two kernels
     const int groups = 4, cols = (G + groups - 1) / groups;
-    kpts_colsum_kernel<<<dim3(R, groups), 256, 0, sb_cs(stream)>>>(x, G, C, cols, w, b, kpts_pred_all);
+    if (x_is_half)
+        kpts_colsum_kernel<__half><<<dim3(R, groups), 256, 0, sb_cs(stream)>>>((const __half*)x, G, C, cols, w, b, kpts_pred_all);
+    else
+        kpts_colsum_kernel<float><<<dim3(R, groups), 256, 0, sb_cs(stream)>>>((const float*)x, G, C, cols, w, b, kpts_pred_all);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     kpts_softmax_kernel<<<R, 96, 0, sb_cs(stream)>>>(kpts_pred_all, G, kpts_prob, left_prob, right_prob);

@@ -17,6 +17,8 @@
 //      two lattice rows are staged in shared memory (each tap = four coalesced 128-bit
 //      channel-vector loads), then averaged and stored as coalesced channel vectors -- the
 //      lattice (69 MB for the 14x14 keypoint pooling) never touches HBM.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -168,6 +170,15 @@ roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int
         o.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, a1.y), __fadd_rn(b0.y, b1.y)), 0.25f);
         o.z = __fmul_rn(__fadd_rn(__fadd_rn(a0.z, a1.z), __fadd_rn(b0.z, b1.z)), 0.25f);
         o.w = __fmul_rn(__fadd_rn(__fadd_rn(a0.w, a1.w), __fadd_rn(b0.w, b1.w)), 0.25f);
+        if (round_tf32 == 2) {      // fp16 output for the kind::f16 convs (same element strides, half the bytes)
+            __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            __half* ob = reinterpret_cast<__half*>(out) + ((size_t)n * P + ph) * P * out_ld + out_coff;
+            *reinterpret_cast<uint2*>(ob + (size_t)pw * out_ld + 4 * c4) = pk;
+            continue;
+        }
         if (round_tf32) {   // the pooled tile is read only by tensor-core convs: make TF32 truncation exact
             o.x = sb_round_tf32(o.x); o.y = sb_round_tf32(o.y); o.z = sb_round_tf32(o.z); o.w = sb_round_tf32(o.w);
         }

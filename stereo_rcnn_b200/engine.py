@@ -22,13 +22,15 @@ def _pack_conv(w):
 
 
 class PackedConv(object):
-    __slots__ = ("w", "scale", "shift", "Cin", "Cout", "kh", "kw", "pad")
+    __slots__ = ("w", "w16", "scale", "shift", "Cin", "Cout", "kh", "kw", "pad")
 
     round_weights = True      # class-wide switch: False keeps exact fp32 weights (SIMT yardstick runs)
+    make_half = False         # class-wide switch: also keep an fp16 copy (fp16-operand mode)
 
     def __init__(self, w, scale, shift, pad):
         self.Cout, self.Cin, self.kh, self.kw = w.shape
         wp = _pack_conv(w).clone()
+        self.w16 = wp.to(torch.float16) if PackedConv.make_half else None    # kind::f16 operand (round to nearest)
         if PackedConv.round_weights:   # round to TF32 (nearest) once: the tensor core would otherwise truncate
             ops.round_tf32_(wp)
         self.w, self.scale, self.shift, self.pad = wp, scale, shift, pad
@@ -37,7 +39,15 @@ class PackedConv(object):
 class StereoRCNNEngine(object):
     """state_dict uses the reference's key names (RCNN_layer1.0.0.conv1.weight, ...)"""
 
-    def __init__(self, state_dict, device="cuda", n_classes=2, conv_impl="auto"):
+    def __init__(self, state_dict, device="cuda", n_classes=2, conv_impl="auto", precision=None):
+        """precision: "tf32" (fp32 storage, kind::tf32) or "fp16" (fp16 conv operands, kind::f16, fp32 accumulate
+        and fp32 residual stream); default from $SB_PRECISION, else "tf32".  conv_impl="simt" forces exact fp32."""
+        import os
+        precision = precision or os.environ.get("SB_PRECISION", "tf32")
+        assert precision in ("tf32", "fp16")
+        self.half = precision == "fp16" and conv_impl != "simt"
+        self.precision = "fp32-simt" if conv_impl == "simt" else precision
+        self.keep32 = False
         self.device = torch.device(device)
         self.n_classes = n_classes
         self.conv_impl = conv_impl
@@ -45,6 +55,7 @@ class StereoRCNNEngine(object):
         # conv_impl="simt" is the exact-fp32 yardstick: exact weights, exact stores, no TF32 hygiene modes
         self.exact = conv_impl == "simt"
         PackedConv.round_weights = not self.exact
+        PackedConv.make_half = self.half
         sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
               if not k.endswith("num_batches_tracked")}
         self.p = {}
@@ -66,6 +77,9 @@ class StereoRCNNEngine(object):
         wst = torch.zeros(64, 160, 1, 1, device=self.device)          # stem as a GEMM over the padded patch matrix
         wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)      # (ci, r, s) order of sb_stem_im2col
         self.p["stem_gemm"] = PackedConv(wst, s, b, 0)
+        wst = torch.zeros(64, 192, 1, 1, device=self.device)          # fp16 variant: three 64-wide K-steps
+        wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)
+        self.p["stem_gemm16"] = PackedConv(wst, s, b, 0)
         for li, nb in enumerate(LAYERS):
             for bi in range(nb):
                 p = "RCNN_layer%d.0.%d" % (li + 1, bi)
@@ -104,22 +118,29 @@ class StereoRCNNEngine(object):
 
     # ------------------------------------------------------------------ helpers
     def _conv(self, x, pc, relu=False, stride=1, residual=None, up_src=None, out=None, out_coff=0,
-              out_strides=None, Cin=None, tag=None, out_mode=ops.EXACT, res_biased=False, in_biased=False):
+              out_strides=None, Cin=None, tag=None, out_mode=ops.EXACT, res_biased=False, in_biased=False,
+              f32=True, f16=False, out16=None):
+        """x fp32 (tf32 / simt modes) or fp16 (fp16 mode).  Returns the fp32 output, the fp16 twin, or both."""
         N, H, W = x.shape[:3]
         Ho = (H + 2 * pc.pad - pc.kh) // stride + 1
         Wo = (W + 2 * pc.pad - pc.kw) // stride + 1
-        if out is None:
+        half_in = x.dtype == torch.float16
+        if out is None and f32:
             out = torch.empty(N, Ho, Wo, pc.Cout, dtype=torch.float32, device=x.device)
-        if self.exact:
+        if out16 is None and f16:
+            out16 = torch.empty(N, Ho, Wo, pc.Cout, dtype=torch.float16, device=x.device)
+        if self.exact or half_in:
             out_mode, res_biased, in_biased = ops.EXACT, False, False
-        d = ops.conv_desc(x, pc.w, out, pc.Cin if Cin is None else Cin, pc.Cout, pc.kh, pc.kw, stride, pc.pad,
-                          Ho, Wo, scale=pc.scale, shift=pc.shift, residual=residual, up_src=up_src, relu=relu,
-                          out_coff=out_coff, out_strides=out_strides, out_mode=out_mode, res_biased=res_biased,
-                          in_biased=in_biased)
-        impl = ops.conv2d(d, self.conv_impl)
+        d = ops.conv_desc(x, pc.w16 if half_in else pc.w, out, pc.Cin if Cin is None else Cin, pc.Cout, pc.kh,
+                          pc.kw, stride, pc.pad, Ho, Wo, scale=pc.scale, shift=pc.shift, residual=residual,
+                          up_src=up_src, relu=relu, out_coff=out_coff, out_strides=out_strides, out_mode=out_mode,
+                          res_biased=res_biased, in_biased=in_biased, out16=out16)
+        impl = ops.conv2d(d, "tc" if half_in else self.conv_impl)
         if tag is not None:
-            self.impl_used[tag] = impl
-        return out
+            self.impl_used[tag] = impl + ("16" if half_in else "")
+        if out is not None and out16 is not None:
+            return out, out16
+        return out if out is not None else out16
 
     def _bottleneck(self, x, prefix, stride, has_ds):
         """resnet.py:82-102; the stride sits on the 1x1 conv1 and on the downsample (Q1)"""
@@ -137,8 +158,18 @@ class StereoRCNNEngine(object):
         return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3",
                           out_mode=ops.BIASED, res_biased=not has_ds)
 
+    def _bottleneck16(self, x32, x16, prefix, stride, has_ds):
+        """fp16-operand variant: convs read fp16 twins, the residual stream itself stays exact fp32"""
+        xin = ops.subsample2(x16) if stride == 2 else x16
+        o = self._conv(xin, self.p[prefix + ".conv1"], relu=True, tag=prefix + ".conv1", f32=False, f16=True)
+        o = self._conv(o, self.p[prefix + ".conv2"], relu=True, tag=prefix + ".conv2", f32=False, f16=True)
+        res = self._conv(xin, self.p[prefix + ".downsample.0"], tag=prefix + ".ds") if has_ds else x32
+        return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3", f16=True)
+
     def trunk_fpn(self, im_nchw):
         """images [N,3,H,W] NCHW -> dict of NHWC C2..C5, P2..P6 (stereo_rcnn.py:155-168)"""
+        if self.half:
+            return self._trunk_fpn16(im_nchw)
         if self.exact:
             c0 = ops.stem_conv(im_nchw, *self.stem, out_mode=ops.EXACT)
         else:       # patch matrix (pixels rounded to TF32) + tcgen05 GEMM
@@ -162,20 +193,49 @@ class StereoRCNNEngine(object):
         feats.update(p2=p2, p3=p3, p4=p4, p5=p5, p6=p6)
         return feats
 
+    def _trunk_fpn16(self, im_nchw):
+        """fp16-operand trunk: every conv input is an fp16 tensor (half the HBM bytes, kind::f16 = 2x the TF32
+        MMA rate, same 11-bit significand); fp32 copies exist only where a non-conv consumer needs them
+        (residual adds, FPN upsample source, RoIAlign, the user-visible P levels)."""
+        c0 = self._conv(ops.stem_im2col16(im_nchw), self.p["stem_gemm16"], relu=True, tag="stem", f32=False, f16=True)
+        c1 = ops.maxpool3x3s2_ceil(c0)
+        feats = {"c1": c1.float() if self.keep32 else None, "c1_16": c1}
+        x32, x16 = None, c1
+        for li, nb in enumerate(LAYERS):
+            for bi in range(nb):
+                x32, x16 = self._bottleneck16(x32, x16, "RCNN_layer%d.0.%d" % (li + 1, bi),
+                                              STRIDES[li] if bi == 0 else 1, bi == 0)
+            feats["c%d" % (li + 2)], feats["c%d_16" % (li + 2)] = x32, x16
+        p5, p5h = self._conv(feats["c5_16"], self.p["RCNN_toplayer"], tag="toplayer", f16=True)
+        t = self._conv(feats["c4_16"], self.p["RCNN_latlayer1"], up_src=p5, tag="lat1", f32=False, f16=True)
+        p4, p4h = self._conv(t, self.p["RCNN_smooth1"], tag="smooth1", f16=True)
+        t = self._conv(feats["c3_16"], self.p["RCNN_latlayer2"], up_src=p4, tag="lat2", f32=False, f16=True)
+        p3, p3h = self._conv(t, self.p["RCNN_smooth2"], tag="smooth2", f16=True)
+        t = self._conv(feats["c2_16"], self.p["RCNN_latlayer3"], up_src=p3, tag="lat3", f32=False, f16=True)
+        p2, p2h = self._conv(t, self.p["RCNN_smooth3"], tag="smooth3", f16=True)
+        feats.update(p2=p2, p3=p3, p4=p4, p5=p5, p6=ops.subsample2(p5), p2_16=p2h, p3_16=p3h, p4_16=p4h,
+                     p5_16=p5h, p6_16=ops.subsample2(p5h))
+        return feats
+
     def rpn(self, feats, B):
         """stereo_rpn.py:73-95 -> cls_prob [B,A,2], bbox_pred [B,A,6], level shapes"""
-        levels = [feats[k] for k in ("p2", "p3", "p4", "p5", "p6")]
+        sfx = "_16" if self.half else ""
+        levels = [feats[k + sfx] for k in ("p2", "p3", "p4", "p5", "p6")]
         shapes = [[f.shape[1], f.shape[2]] for f in levels]
         P = sum(h * w for h, w in shapes)
         dev = self.device
         head = torch.empty(B, P, 32, dtype=torch.float32, device=dev)
         off = 0
         for f, (h, w) in zip(levels, shapes):
-            cat = torch.empty(B, h, w, 1024, dtype=torch.float32, device=dev)
-            for side in range(2):   # shared RPN_Conv on L then R, channel-concatenated (Q6)
-                self._conv(f[side * B:(side + 1) * B], self.p["RCNN_rpn.RPN_Conv"], relu=True, out=cat,
-                           out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv",
-                           out_mode=ops.ROUND_TF32)
+            cat = torch.empty(B, h, w, 1024, dtype=f.dtype, device=dev)
+            kw = dict(f32=False, out16=cat) if self.half else dict(out=cat, out_mode=ops.ROUND_TF32)
+            if B == 1:      # L and R in one launch: image index n = side -> channel offset n * 512
+                self._conv(f, self.p["RCNN_rpn.RPN_Conv"], relu=True, out_strides=(512, w * 1024, 1024),
+                           tag="rpn_conv", **kw)
+            else:
+                for side in range(2):   # shared RPN_Conv on L then R, channel-concatenated (Q6)
+                    self._conv(f[side * B:(side + 1) * B], self.p["RCNN_rpn.RPN_Conv"], relu=True,
+                               out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv", **kw)
             self._conv(cat, self.p["rpn_heads"], out=head[:, off:off + h * w],
                        out_strides=(P * 32, w * 32, 32), tag="rpn_heads")
             off += h * w
@@ -189,22 +249,27 @@ class StereoRCNNEngine(object):
         fr = [feats[k][B:] for k in mk]
         R = rois_l.shape[0]
         dev = self.device
-        pooled = torch.empty(R, 7, 7, 512, dtype=torch.float32, device=dev)
-        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0, round_tf32=not self.exact)
-        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256, round_tf32=not self.exact)
+        h = self.half
+        adt = torch.float16 if h else torch.float32
+        rt = not self.exact and not h
+        c16 = dict(f32=False, f16=True) if h else {}
+        pooled = torch.empty(R, 7, 7, 512, dtype=adt, device=dev)
+        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0, round_tf32=rt, half=h)
+        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256, round_tf32=rt, half=h)
         x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0",
-                       out_mode=ops.ROUND_TF32)
+                       out_mode=ops.ROUND_TF32, **c16)
         fc7 = self._conv(x, self.p["RCNN_top.3"], relu=True, tag="top3").view(R, 2048)
         cls_prob, bbox, dim = ops.box_tail(fc7, *self.fc, n_classes=self.n_classes)
-        pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14, round_tf32=not self.exact)
+        pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14, round_tf32=rt, half=h)
         x = pk
         for i in range(0, 12, 2):
-            x = self._conv(x, self.p["RCNN_kpts.%d" % i], relu=True, tag="kpts%d" % i, out_mode=ops.ROUND_TF32)
-        up = torch.empty(R, 28, 28, 256, dtype=torch.float32, device=dev)
+            x = self._conv(x, self.p["RCNN_kpts.%d" % i], relu=True, tag="kpts%d" % i, out_mode=ops.ROUND_TF32, **c16)
+        up = torch.empty(R, 28, 28, 256, dtype=adt, device=dev)
         for a in range(2):
             for b in range(2):
-                self._conv(x, self.deconv[a][b], relu=True, out=up[:, a:, b:],
-                           out_strides=(28 * 28 * 256, 2 * 28 * 256, 2 * 256), tag="deconv")
+                kw = dict(f32=False, out16=up[:, a:, b:]) if h else dict(out=up[:, a:, b:])
+                self._conv(x, self.deconv[a][b], relu=True, out_strides=(28 * 28 * 256, 2 * 28 * 256, 2 * 256),
+                           tag="deconv", **kw)
         kp, lb, rb, ka = ops.kpts_tail(up, *self.kpts_class, want_pred_all=True)
         return dict(pooled_box=pooled, pooled_kpts=pk, fc7=fc7, cls_prob=cls_prob, bbox_pred=bbox,
                     dim_orien_pred=dim, kpts_prob=kp, left_border_prob=lb, right_border_prob=rb,
@@ -228,7 +293,9 @@ class StereoRCNNEngine(object):
         out["bbox_pred"] = out["bbox_pred"].view(B, n, -1)
         out["dim_orien_pred"] = out["dim_orien_pred"].view(B, n, -1)
         if keep_features:      # debugging / tests: exact-fp32 views of the pre-biased trunk tensors
-            out["feats"] = {k: (ops.unbias(v) if (k[0] == "c" and not self.exact) else v) for k, v in feats.items()}
+            ub = not self.exact and not self.half
+            out["feats"] = {k: (ops.unbias(v) if (k[0] == "c" and ub and v is not None and v.dtype == torch.float32)
+                                else v) for k, v in feats.items()}
             out["feats_raw"] = feats
         return out
 

@@ -31,7 +31,8 @@ class ConvDesc(ctypes.Structure):
                 ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("Ho", c_int), ("Wo", c_int),
                 ("in_ld", c_int), ("res_ld", c_int), ("UH", c_int), ("UW", c_int), ("relu", c_int),
                 ("out_coff", c_int), ("out_mode", c_int), ("res_biased", c_int), ("in_biased", c_int),
-                ("out_n_stride", c_ll), ("out_h_stride", c_ll), ("out_w_stride", c_ll)]
+                ("out_n_stride", c_ll), ("out_h_stride", c_ll), ("out_w_stride", c_ll),
+                ("out16", c_void_p), ("in_dtype", c_int), ("reserved0", c_int)]
 
 
 _SIGS = {
@@ -61,9 +62,11 @@ _SIGS = {
     "sb_conv2d_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "sb_stem_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sb_stem_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sb_stem_im2col16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sb_maxpool3x3s2_ceil16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sb_maxpool3x3s2_ceil": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sb_subsample2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "sb_kpts_tail": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "sb_kpts_tail": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
     "sb_box_tail": (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p]),
     "sb_test_decode": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int] + [c_void_p] * 4 + [c_void_p]),

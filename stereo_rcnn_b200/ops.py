@@ -94,18 +94,22 @@ def roi_align_backward(ah, aw, scale, top_grad, rois, bottom_grad):
     return 1
 
 
-def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0, round_tf32=False):
-    """feats: 4 NHWC tensors (P2..P5); rois [R,5]; -> out [R,pooled,pooled,out_ld] NHWC"""
+def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0, round_tf32=False, half=False):
+    """feats: 4 NHWC fp32 tensors (P2..P5); rois [R,5]; -> out [R,pooled,pooled,out_ld] NHWC (fp32, fp32 rounded
+    to TF32, or fp16 when half=True)"""
     L = _l.load()
     C = feats[0].shape[3]
     R = rois.shape[0]
     if out is None:
-        out = torch.empty(R, pooled, pooled, C, dtype=torch.float32, device=rois.device)
+        out = torch.empty(R, pooled, pooled, C, dtype=torch.float16 if half else torch.float32, device=rois.device)
+    if half:
+        assert out.dtype == torch.float16
+        round_tf32 = 2
     fp = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in feats])
     hs = (ctypes.c_int * 4)(*[f.shape[1] for f in feats])
     ws_ = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
     check(L.sb_roi_align_pyramid_nhwc(fp, hs, ws_, C, float(im_h), ptr(_f32c(rois)), R, pooled, ptr(out),
-                                      out.shape[3], out_coff, 1 if round_tf32 else 0, stream_ptr()),
+                                      out.shape[3], out_coff, int(round_tf32), stream_ptr()),
           "sb_roi_align_pyramid_nhwc")
     return out
 
@@ -187,12 +191,16 @@ def dense_align(calib4, scale, im_left, im_right, box_left, keypoints, poses):
 # ------------------------------------------------------------- layer ops ----
 def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, shift=None, residual=None,
               up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None, out_mode=0, res_biased=False,
-              in_biased=False):
+              in_biased=False, out16=None):
     """x: NHWC [N,H,W,in_ld]; wgt packed [Cout,kh,kw,Cin]; out: any tensor addressed through out_strides
     = (n, h, w) strides in floats (default: dense NHWC of out.shape[-1] channels)."""
     d = ConvDesc()
     N, H, W = x.shape[0], x.shape[1], x.shape[2]
-    d.in_, d.wgt, d.out = x.data_ptr(), wgt.data_ptr(), out.data_ptr()
+    d.in_, d.wgt = x.data_ptr(), wgt.data_ptr()
+    d.out = out.data_ptr() if out is not None else None
+    d.out16 = out16.data_ptr() if out16 is not None else None
+    d.in_dtype = 1 if x.dtype == torch.float16 else 0
+    assert wgt.dtype == x.dtype, "weights and activations of a conv share one operand type"
     d.scale = scale.data_ptr() if scale is not None else None
     d.shift = shift.data_ptr() if shift is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
@@ -206,7 +214,7 @@ def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, s
     d.out_coff = out_coff
     d.out_mode, d.res_biased, d.in_biased = int(out_mode), int(bool(res_biased)), int(bool(in_biased))
     if out_strides is None:
-        ld = out.shape[-1]
+        ld = (out if out is not None else out16).shape[-1]
         out_strides = (Ho * Wo * ld, Wo * ld, ld)
     d.out_n_stride, d.out_h_stride, d.out_w_stride = [int(s) for s in out_strides]
     return d
@@ -243,6 +251,16 @@ def stem_im2col(im_nchw):
     return out
 
 
+def stem_im2col16(im_nchw):
+    """-> fp16 [N, Ho, Wo, 192] patch matrix of the stem (147 taps zero-padded to 192)"""
+    L = _l.load()
+    N, _, H, W = im_nchw.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty(N, Ho, Wo, 192, dtype=torch.float16, device=im_nchw.device)
+    check(L.sb_stem_im2col16(ptr(_f32c(im_nchw)), N, H, W, ptr(out), stream_ptr()), "sb_stem_im2col16")
+    return out
+
+
 def maxpool3x3s2_ceil(x):
     L = _l.load()
     N, H, W, C = x.shape
@@ -250,16 +268,21 @@ def maxpool3x3s2_ceil(x):
     def osz(v):
         o = (v - 3 + 1) // 2 + 1
         return o - 1 if (o - 1) * 2 >= v else o
-    out = torch.empty(N, osz(H), osz(W), C, dtype=torch.float32, device=x.device)
-    check(L.sb_maxpool3x3s2_ceil(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_maxpool3x3s2_ceil")
+    out = torch.empty(N, osz(H), osz(W), C, dtype=x.dtype, device=x.device)
+    if x.dtype == torch.float16:
+        check(L.sb_maxpool3x3s2_ceil16(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_maxpool3x3s2_ceil16")
+    else:
+        check(L.sb_maxpool3x3s2_ceil(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_maxpool3x3s2_ceil")
     return out
 
 
 def subsample2(x):
+    """x[:, ::2, ::2, :]; a pure copy, so fp16 tensors go through the same kernel viewed as C/2 fp32 lanes"""
     L = _l.load()
     N, H, W, C = x.shape
-    out = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=torch.float32, device=x.device)
-    check(L.sb_subsample2(ptr(x), N, H, W, C, ptr(out), stream_ptr()), "sb_subsample2")
+    out = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, dtype=x.dtype, device=x.device)
+    cw = C // 2 if x.dtype == torch.float16 else C
+    check(L.sb_subsample2(ptr(x), N, H, W, cw, ptr(out), stream_ptr()), "sb_subsample2")
     return out
 
 
@@ -271,7 +294,8 @@ def kpts_tail(x, w, b, want_pred_all=False):
     lp = torch.empty(R, G, dtype=torch.float32, device=dev)
     rp = torch.empty(R, G, dtype=torch.float32, device=dev)
     ka = torch.empty(R, 6, G, dtype=torch.float32, device=dev)      # logits; also the staging between the 2 kernels
-    check(L.sb_kpts_tail(ptr(x), R, G, C, ptr(w), ptr(b), ptr(kp), ptr(lp), ptr(rp), ptr(ka), stream_ptr()),
+    check(L.sb_kpts_tail(ptr(x), 1 if x.dtype == torch.float16 else 0, R, G, C, ptr(w), ptr(b), ptr(kp), ptr(lp),
+                         ptr(rp), ptr(ka), stream_ptr()),
           "sb_kpts_tail")
     return kp, lp, rp, ka
 

@@ -42,7 +42,7 @@ def test_python_binding_matches_header(so_path):
 def test_struct_layout_matches_c(so_path):
     """sizeof of the ctypes mirrors equals what the header implies (catches field drift)"""
     from stereo_rcnn_b200.lib import ConvDesc, ProposalCfg
-    assert ctypes.sizeof(ConvDesc) == 7 * 8 + 20 * 4 + 3 * 8              # 7 ptrs, 20 ints, 3 long long
+    assert ctypes.sizeof(ConvDesc) == 7 * 8 + 20 * 4 + 3 * 8 + 8 + 2 * 4  # 7 ptrs, 20 ints, 3 long long, out16, 2 ints
     assert ctypes.sizeof(ProposalCfg) == 4 + 64 + 32 + 32 + 4 + 32 + 4 + 4 + 4 + 4  # incl. 8-byte alignment pads
 
 

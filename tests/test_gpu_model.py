@@ -48,20 +48,28 @@ def close(a, b, impl):
     return l2_err(a, b) < 1e-3 and rel_err(a, b) < 1.5e-3
 
 
-def run_conv(x, w, impl, stride=1, pad=0, scale=None, shift=None, residual=None, up_src=None, relu=False):
-    """x NCHW cpu, w [Co,Ci,kh,kw] cpu -> NCHW cpu result through the C ABI"""
+def run_conv(x, w, impl, stride=1, pad=0, scale=None, shift=None, residual=None, up_src=None, relu=False,
+             half=False, twin=False):
+    """x NCHW cpu, w [Co,Ci,kh,kw] cpu -> NCHW cpu result through the C ABI (half: fp16 operands, kind::f16;
+    twin: also return the fp16 twin output)"""
     Co, Ci, kh, kw = w.shape
     xg = cu(nhwc(x))
+    wg = cu(w.permute(0, 2, 3, 1))
+    if half:
+        xg, wg = xg.half(), wg.half()
     N, H, W = xg.shape[:3]
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     out = torch.empty(N, Ho, Wo, Co, device="cuda")
-    d = G.conv_desc(xg, cu(w.permute(0, 2, 3, 1)), out, Ci, Co, kh, kw, stride, pad, Ho, Wo,
+    out16 = torch.empty(N, Ho, Wo, Co, device="cuda", dtype=torch.float16) if twin else None
+    d = G.conv_desc(xg, wg, out, Ci, Co, kh, kw, stride, pad, Ho, Wo, out16=out16,
                     scale=None if scale is None else cu(scale), shift=None if shift is None else cu(shift),
                     residual=None if residual is None else cu(nhwc(residual)),
                     up_src=None if up_src is None else cu(nhwc(up_src)), relu=relu)
     used = G.conv2d(d, impl)
     assert used == impl
     torch.cuda.synchronize()
+    if twin:
+        return out.permute(0, 3, 1, 2).cpu(), out16.float().permute(0, 3, 1, 2).cpu()
     return out.permute(0, 3, 1, 2).cpu()
 
 
@@ -138,6 +146,27 @@ def test_conv_tc_tf32(case):
         assert rel_err(y, ref_conv(x, w, 1, p, None, sh, residual=res)) < 1e-3
         y = run_conv(x, w, "tc", 1, p, None, sh, up_src=up, relu=True)
         assert rel_err(y, ref_conv(x, w, 1, p, None, sh, up_src=up, relu=True)) < 1e-3
+
+
+@pytest.mark.parametrize("case", [c for c in TC_CASES if c[1] % 64 == 0])
+def test_conv_tc_fp16_operands(case):
+    """kind::f16 path: fp16 operands (11-bit significand, like TF32), fp32 accumulate, fp32 + fp16 twin outputs"""
+    N, Ci, H, W, Co, k = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+    p = k // 2
+    xr, wr = x.half().float(), w.half().float()            # the operands the tensor core actually sees
+    y, y16 = run_conv(x, w, "tc", 1, p, sc, sh, relu=True, half=True, twin=True)
+    ref = ref_conv(xr, wr, 1, p, sc, sh, relu=True)
+    assert rel_err(y, ref) < 2e-5                           # exact products, fp32 accumulation order only
+    assert rel_err(y16, ref) < 1e-3
+    assert rel_err(y, ref_conv(x, w, 1, p, sc, sh, relu=True)) < 1e-3
+    if N * H * W * Co < 4e6:
+        res = torch.randn(N, Co, H, W, generator=g)
+        y = run_conv(x, w, "tc", 1, p, None, sh, residual=res, half=True)
+        assert rel_err(y, ref_conv(xr, wr, 1, p, None, sh, residual=res)) < 2e-5
 
 
 def test_conv_tc_strided_outputs():
@@ -224,12 +253,13 @@ def test_forward_small_vs_oracle_and_reference_golden(golden_dir):
     info = torch.tensor([[float(H), float(W), 1.0]])
     o = OM.forward(sd, iml, imr, info)                                  # CPU oracle, every stage
     impl = os.environ.get("SB_CONV_IMPL", "auto")
-    eng = E.StereoRCNNEngine(sd, "cuda", conv_impl=impl)
+    eng = E.StereoRCNNEngine(sd, "cuda", conv_impl=impl)       # precision from $SB_PRECISION (tf32 | fp16)
+    print("precision:", eng.precision)
     r = eng.forward(iml.cuda(), imr.cuda(), info.cuda(), keep_features=True)
     torch.cuda.synchronize()
     # stage 1: trunk + FPN (left image = batch 0, right = batch 1)
     for k in ("c2", "c3", "c4", "c5", "p5", "p4", "p3", "p2", "p6"):
-        got = r["feats"][k].permute(0, 3, 1, 2).cpu().numpy()
+        got = r["feats"][k].float().permute(0, 3, 1, 2).cpu().numpy()
         assert close(got[0:1], o["left"][k].numpy(), impl), k
         assert close(got[1:2], o["right"][k].numpy(), impl), k
     # stage 2: RPN head
@@ -242,8 +272,8 @@ def test_forward_small_vs_oracle_and_reference_golden(golden_dir):
     # stage 4: heads on the oracle's rois (identical inputs) within 1e-3
     h = eng.heads(r["feats_raw"], 1, rl.view(-1, 5), rr.view(-1, 5), float(H))
     torch.cuda.synchronize()
-    assert close(h["pooled_box"].permute(0, 3, 1, 2).cpu().numpy(), o["pooled_box"].numpy(), impl)
-    assert close(h["pooled_kpts"].permute(0, 3, 1, 2).cpu().numpy(), o["pooled_kpts"].numpy(), impl)
+    assert close(h["pooled_box"].float().permute(0, 3, 1, 2).cpu().numpy(), o["pooled_box"].numpy(), impl)
+    assert close(h["pooled_kpts"].float().permute(0, 3, 1, 2).cpu().numpy(), o["pooled_kpts"].numpy(), impl)
     for k in ("fc7", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_pred_all", "kpts_prob", "left_border_prob",
               "right_border_prob"):
         assert close(h[k].cpu().numpy().reshape(o[k].shape), o[k].numpy(), impl), k
@@ -258,6 +288,12 @@ def test_forward_small_vs_oracle_and_reference_golden(golden_dir):
     print("end-to-end proposal set overlap: %.3f" % frac)
     assert frac >= (0.98 if impl == "simt" else 0.5)
 
+
+
+def test_forward_small_fp16_operand_path(golden_dir, monkeypatch):
+    """the kind::f16 mode (fp16 conv operands, fp32 accumulate + fp32 residual stream) meets the same bars"""
+    monkeypatch.setenv("SB_PRECISION", "fp16")
+    test_forward_small_vs_oracle_and_reference_golden(golden_dir)
 
 
 def test_forward_small_exact_fp32_simt_path(golden_dir, monkeypatch):

@@ -27,9 +27,11 @@ def main():
     eng = E.StereoRCNNEngine(sd, "cuda", conv_impl=impl)
     r = eng.forward(iml.cuda(), imr.cuda(), info.cuda(), keep_features=True)
     torch.cuda.synchronize()
-    print("impl", impl, sorted(set(eng.impl_used.values())))
+    print("impl", impl, eng.precision, sorted(set(eng.impl_used.values())))
     for k in ("c1", "c2", "c3", "c4", "c5", "p5", "p4", "p3", "p2"):
-        got = r["feats"][k].permute(0, 3, 1, 2).cpu().numpy()
+        if r["feats"].get(k) is None:
+            continue
+        got = r["feats"][k].float().permute(0, 3, 1, 2).cpu().numpy()
         print("%-6s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(got[0:1], o["left"][k].numpy())))
     for k in ("rpn_cls_prob", "rpn_bbox_pred"):
         print("%-14s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(r[k].cpu().numpy(), o[k].numpy())))
@@ -39,7 +41,7 @@ def main():
     h = eng.heads(r["feats_raw"], 1, o["rois_left"].cuda().view(-1, 5), o["rois_right"].cuda().view(-1, 5), float(H))
     torch.cuda.synchronize()
     for k in ("pooled_box", "pooled_kpts"):
-        print("%-14s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(h[k].permute(0, 3, 1, 2).cpu().numpy(), o[k].numpy())))
+        print("%-14s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(h[k].float().permute(0, 3, 1, 2).cpu().numpy(), o[k].numpy())))
     for k in ("fc7", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_pred_all", "kpts_prob", "left_border_prob"):
         print("%-14s max-rel %.2e  l2-rel %.2e" % ((k,) + rel(h[k].cpu().numpy().reshape(o[k].shape), o[k].numpy())))
 
