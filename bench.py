@@ -244,11 +244,11 @@ def run_ours(args):
         pk = peaks()
         conv_ms = conv_time_per_step(pipe, iml, imr)
         tflops = 2 * TC_GMACS_PER_PAIR * 1e9 / (conv_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM, all conv/FC launches of one step)",
+        half = pipe.eng.half
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::%s implicit GEMM, all conv/FC launches of one step)" % ("f16" if half else "tf32"),
                 "achieved": round(tflops, 2), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": round(tflops / pk["bf16_tflops_sustained"], 4), "traffic": None,
-                "peak_source": pk["src"] + " cuBLAS bf16 sustained (kind::tf32 issues at half that rate)",
-                "frac_of_tf32_rate": round(tflops / (pk["bf16_tflops_sustained"] / 2), 4),
+                "peak_source": pk["src"] + " cuBLAS bf16 sustained" + ("" if half else " (kind::tf32 issues at half that rate)"),
                 "conv_ms_per_step": round(conv_ms, 3), "share_of_step": round(conv_ms / ms_per_step, 3)}
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_sample()
@@ -260,7 +260,7 @@ def run_ours(args):
     out = {
         "metric": "stereo pairs/sec (1242x375)", "value": round(value, 3), "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": pipe.eng.precision + (" operands (tcgen05 kind::f16), fp32 accumulate, fp32 residual stream/outputs" if pipe.eng.half else " (fp32 storage, kind::tf32, fp32 accumulate)"),
         "data": "synthetic",
         "config": {"workload": "configs[1]: batch-1 inference per GPU, synthetic KITTI-shape pair 2x[1,3,600,1987], "
                                "full pipeline incl. dense_align (D=%d synthetic poses)" % D_ALIGN,
