@@ -273,47 +273,60 @@ stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, in
     out[e] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// fp16 variant for the kind::f16 GEMM: rows of 192 halves (147 taps, zero padded to 3 K-steps of 64);
-// one thread = 8 consecutive k (one 16-byte store)
+// fp16 variant for the kind::f16 GEMM: rows of 192 halves (147 taps, zero padded to 3 K-steps of 64).
+// One CTA = 64 consecutive output pixels of one output row: the 7 x 3 input rows it needs (133 columns
+// each) are staged in shared memory with coalesced loads, then every thread emits 16-byte stores.
+constexpr int kI2cPix = 64;
 __global__ void __launch_bounds__(256)
 stem_im2col16_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo, uint4* __restrict__ out) {
-    const long long total = (long long)N * Ho * Wo * 24;
-    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (e >= total) return;
-    const int g = (int)(e % 24);
-    long long t = e / 24;
-    const int wo = (int)(t % Wo); t /= Wo;
-    const int ho = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+    constexpr int SW = 2 * kI2cPix + 5;            // staged columns
+    __shared__ float tile[3 * 7][SW + 1];
+    const int segs = (Wo + kI2cPix - 1) / kI2cPix;
+    const int seg = blockIdx.x % segs;
+    const int ho = (blockIdx.x / segs) % Ho;
+    const int n = blockIdx.x / (segs * Ho);
+    const int wo0 = seg * kI2cPix;
+    const int wi0 = wo0 * 2 - 3, hi0 = ho * 2 - 3;
     const float* base = im + (long long)n * 3 * H * W;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = g * 8 + j;
-        float x = 0.f;
-        if (k < 147) {
-            const int ci = k / 49, tap = k - ci * 49;
-            const int r = tap / 7, s2 = tap - r * 7;
-            const int hi = ho * 2 - 3 + r, wi = wo * 2 - 3 + s2;
-            if (hi >= 0 && hi < H && wi >= 0 && wi < W) x = __ldg(base + ((long long)ci * H + hi) * W + wi);
-        }
-        v[j] = x;
+    for (int e = threadIdx.x; e < 21 * SW; e += 256) {
+        const int row = e / SW, col = e - row * SW;
+        const int ci = row / 7, r = row - ci * 7;
+        const int hi = hi0 + r, wi = wi0 + col;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(base + ((long long)ci * H + hi) * W + wi);
+        tile[row][col] = v;
     }
-    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-    out[e] = o;
+    __syncthreads();
+    const int npix = min(kI2cPix, Wo - wo0);
+    for (int e = threadIdx.x; e < npix * 24; e += 256) {
+        const int px = e / 24, g = e - px * 24;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float x = 0.f;
+            if (k < 147) {
+                const int row = k / 7, s2 = k - row * 7;      // row = ci*7 + r
+                x = tile[row][2 * px + s2];
+            }
+            v[j] = x;
+        }
+        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        out[(((long long)n * Ho + ho) * Wo + wo0 + px) * 24 + g] = o;
+    }
 }
 
 }  // namespace
 
 extern "C" int sb_stem_im2col16(const float* im_nchw, int N, int H, int W, void* out_half, sb_stream_t stream) {
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-    const long long total = (long long)N * Ho * Wo * 24;
-    if (total <= 0) return SB_EINVAL;
-    stem_im2col16_kernel<<<sb_div_up(total, 256), 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, (uint4*)out_half);
+    const long long blocks = (long long)N * Ho * ((Wo + kI2cPix - 1) / kI2cPix);
+    if (blocks <= 0) return SB_EINVAL;
+    stem_im2col16_kernel<<<(unsigned)blocks, 256, 0, sb_cs(stream)>>>(im_nchw, N, H, W, Ho, Wo, (uint4*)out_half);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -595,7 +595,9 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     if (!sb_conv2d_tc_supported(d)) return SB_EINVAL;
     TcParams p;
     p.d = *d;
-    p.patch = (d->kh == 3) ? 1 : 0;
+    // spatial 8x16 tiles for 3x3 convs, and for the FPN laterals so that the bilinear upsample taps of a tile
+    // (5x9 source pixels) stay in L1 instead of being re-fetched from L2 for every output row
+    p.patch = (d->kh == 3 || d->up_src) ? 1 : 0;
     p.M = (long long)d->N * d->Ho * d->Wo;
     if (p.M == 0) return SB_OK;
     const bool f16 = d->in_dtype == 1;

@@ -142,6 +142,37 @@ kpts_colsum_kernel(const T* __restrict__ x, int G, int C, int cols_per_cta, cons
     }
 }
 
+// fp16 input: one warp per column, one 16-byte vector (8 channels) per lane and row; C == 256
+__global__ void __launch_bounds__(256)
+kpts_colsum16_kernel(const __half* __restrict__ x, int G, int C, const float* __restrict__ w,
+                     const float* __restrict__ b, float* __restrict__ pred_all) {
+    const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.y * 8 + warp;
+    if (col >= G) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)r * G * G * C) + lane;
+    const int C8 = C >> 3;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int h = 0; h < G; ++h) {
+        const uint4 v = __ldg(xr + ((size_t)h * G + col) * C8);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        s[0] += f0.x; s[1] += f0.y; s[2] += f1.x; s[3] += f1.y;
+        s[4] += f2.x; s[5] += f2.y; s[6] += f3.x; s[7] += f3.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float* wj = w + j * C + lane * 8;
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p = fmaf(wj[e], s[e], p);
+        p = warp_sum(p);
+        if (lane == 0) pred_all[((size_t)r * 6 + j) * G + col] = p + (float)G * b[j];
+    }
+}
+
 __global__ void __launch_bounds__(96)
 kpts_softmax_kernel(const float* __restrict__ pred_all, int G, float* __restrict__ kpts_prob,
                     float* __restrict__ left_prob, float* __restrict__ right_prob) {
@@ -365,7 +396,9 @@ extern "C" int sb_kpts_tail(const void* x, int x_is_half, int R, int G, int C, c
     if (R == 0) return SB_OK;
     if (!kpts_pred_all) return SB_EINVAL;     // [R,6,G] logits are also the staging buffer between the two kernels
     const int groups = 4, cols = (G + groups - 1) / groups;
-    if (x_is_half)
+    if (x_is_half && C == 256)
+        kpts_colsum16_kernel<<<dim3(R, (G + 7) / 8), 256, 0, sb_cs(stream)>>>((const __half*)x, G, C, w, b, kpts_pred_all);
+    else if (x_is_half)
         kpts_colsum_kernel<__half><<<dim3(R, groups), 256, 0, sb_cs(stream)>>>((const __half*)x, G, C, cols, w, b, kpts_pred_all);
     else
         kpts_colsum_kernel<float><<<dim3(R, groups), 256, 0, sb_cs(stream)>>>((const float*)x, G, C, cols, w, b, kpts_pred_all);
