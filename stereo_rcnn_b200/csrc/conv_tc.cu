@@ -35,8 +35,7 @@ constexpr int BLOCK_M = 128;
 constexpr int kRowBytes = 128;  // one swizzle row per pixel per K-step: 32 fp32 (kind::tf32, K=8 per MMA)
                                 // or 64 fp16 (kind::f16, K=16 per MMA); four MMAs per K-step either way
 constexpr int TW = 16, TH = 8;  // spatial patch of a 3x3 tile (TW*TH == BLOCK_M)
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = 64 + 32 * kNumEpiWarps;
+// epilogue warps per CTA: 8 (one big CTA per SM) or 4 ("small" variant: two CTAs per SM for layers with few tiles)
 constexpr int kMaxCout = 2048;   // scale/shift staged in shared memory
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -161,7 +160,7 @@ struct RowInfo {          // per accumulator row of the current tile (one per la
     int pad;
 };
 
-constexpr size_t kEpiSmem = (size_t)kNumEpiWarps * (32 * 8 * 16 + 32 * sizeof(RowInfo));
+constexpr size_t epi_smem(int ew) { return (size_t)ew * (32 * 8 * 16 + 32 * sizeof(RowInfo)); }
 
 struct TcParams {
     sb_conv_desc d;
@@ -173,8 +172,8 @@ struct TcParams {
     long long M;
 };
 
-template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p) {
     constexpr uint32_t kABytes = BLOCK_M * kRowBytes, kBBytes = BLOCK_N * kRowBytes;
@@ -192,7 +191,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [Cout rounded up to BLOCK_N]
     float* s_shift = s_scale + kMaxCout;
     float4* epi_stage = reinterpret_cast<float4*>(s_shift + kMaxCout);            // [8 warps][32 rows][8 float4]
-    RowInfo* epi_rows = reinterpret_cast<RowInfo*>(epi_stage + kNumEpiWarps * 32 * 8);   // [8 warps][32]
+    RowInfo* epi_rows = reinterpret_cast<RowInfo*>(epi_stage + EW * 32 * 8);   // [EW warps][32]
+    constexpr int kNumThreads = 64 + 32 * EW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const sb_conv_desc& d = p.d;
@@ -204,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) {
         if (elect_one()) {
             for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kNumEpiWarps); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EW); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -305,8 +305,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // row addressing is hoisted to once per tile and the residual / upsample paths are compile-time.
         const int q = warp & 3;
         const int ew = warp - 2;
-        const int half = ew >> 2;
-        constexpr int kColsPerWarp = BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32;
+        const int half = EW == 8 ? (ew >> 2) : 0;
+        constexpr int kColsPerWarp = EW == 8 ? (BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32) : BLOCK_N;
         const int col_begin = half * kColsPerWarp;
         const bool has_cols = col_begin < BLOCK_N;
         float4* stg = epi_stage + ew * (32 * 8);
@@ -519,13 +519,16 @@ int pick_block_n(int cout, long long m_tiles, int num_sms) {
     return c256 <= c128 ? 256 : 128;
 }
 
-template <int BN, int ST, bool RES, bool UP, bool IN16>
+template <int BN, int ST, bool RES, bool UP, bool IN16, int EW>
 int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    static_assert((size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem <= 227 * 1024, "smem budget");
-    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + kEpiSmem;
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + epi_smem(EW);
+    static_assert(smem * (EW == 4 ? 2 : 1) <= 227 * 1024, "smem budget");
+    constexpr int kNumThreads = 64 + 32 * EW;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP, IN16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && EW == 4)
+            e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP, IN16, EW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -537,7 +540,8 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
         if (num_sms <= 0) num_sms = 148;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < num_sms ? tiles : num_sms;
+    const int slots = num_sms * (EW == 4 ? 2 : 1);
+    const int grid = tiles < slots ? tiles : slots;
     static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -549,22 +553,22 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, ST, RES, UP, IN16>, ma, mb, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, ST, RES, UP, IN16, EW>, ma, mb, p);
     SB_LAUNCHED();
     if (le != cudaSuccess) return (int)le;
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
 
-template <int BN, int ST>
+template <int BN, int ST, int EW>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
     const bool res = p.d.residual != nullptr, up = p.d.up_src != nullptr;   // never both (supported())
     if (p.d.in_dtype == 1) {
-        if (up) return launch_t<BN, ST, false, true, true>(ma, mb, p, st);
-        return res ? launch_t<BN, ST, true, false, true>(ma, mb, p, st) : launch_t<BN, ST, false, false, true>(ma, mb, p, st);
+        if (up) return launch_t<BN, ST, false, true, true, EW>(ma, mb, p, st);
+        return res ? launch_t<BN, ST, true, false, true, EW>(ma, mb, p, st) : launch_t<BN, ST, false, false, true, EW>(ma, mb, p, st);
     }
-    if (up) return launch_t<BN, ST, false, true, false>(ma, mb, p, st);
-    return res ? launch_t<BN, ST, true, false, false>(ma, mb, p, st) : launch_t<BN, ST, false, false, false>(ma, mb, p, st);
+    if (up) return launch_t<BN, ST, false, true, false, EW>(ma, mb, p, st);
+    return res ? launch_t<BN, ST, true, false, false, EW>(ma, mb, p, st) : launch_t<BN, ST, false, false, false, EW>(ma, mb, p, st);
 }
 
 }  // namespace
@@ -617,7 +621,12 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     }
     int BN = pick_block_n(d->Cout, p.num_m_tiles, sms);
     if (d->residual && BN == 256) BN = 128;   // residual layers are HBM-bound; the 256-wide residual epilogue spills
-    if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256) BN = v; }
+    // "small" variant (128x128 tiles, half the shared memory, two CTAs per SM): measured slower than the
+    // one-CTA-per-SM tiles on every layer shape of this network (tools/conv_bench.py), so it is opt-in only
+    bool small = false;
+    if (const char* e = getenv("SB_TC_SMALL")) small = atoi(e) != 0 && d->Cout >= 128 && !d->up_src;
+    if (small) BN = 128;
+    if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256 && !small) BN = v; }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
     CUtensorMap ma, mb;
     if (p.patch) {
@@ -640,10 +649,11 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         if (!make_map(&mb, d->wgt, 2, dims, strides, box, f16)) return SB_EINVAL;
     }
     cudaStream_t st = sb_cs(stream);
+    if (small) return launch<128, 2, 4>(ma, mb, p, st);
     switch (BN) {
-        case 32: return launch<32, 6>(ma, mb, p, st);
-        case 64: return launch<64, 6>(ma, mb, p, st);
-        case 256: return launch<256, 3>(ma, mb, p, st);
-        default: return launch<128, 4>(ma, mb, p, st);
+        case 32: return launch<32, 6, 8>(ma, mb, p, st);
+        case 64: return launch<64, 6, 8>(ma, mb, p, st);
+        case 256: return launch<256, 3, 8>(ma, mb, p, st);
+        default: return launch<128, 4, 8>(ma, mb, p, st);
     }
 }

@@ -50,17 +50,26 @@ def main():
     for name, N, H, W, Ci, Co, k, res in SHAPES:
         if only and only not in name:
             continue
+        half = os.environ.get("CB_HALF", "1") == "1" and Ci % 64 == 0
         x = torch.randn(N, H, W, Ci, device=dev)
         w = torch.randn(Co, k, k, Ci, device=dev) * 0.05
+        if half:
+            x, w = x.half(), w.half()
         sc = torch.rand(Co, device=dev) + 0.5
         sh = torch.randn(Co, device=dev)
         out = torch.empty(N, H, W, Co, device=dev)
         r = torch.randn(N, H, W, Co, device=dev) if res else None
         line = "%-28s" % name
-        for bn in ("128", "256"):
+        for bn in ("128", "256", "small"):
             if Co < 256 and bn == "256":
                 continue
-            os.environ["SB_TC_BLOCK_N"] = bn
+            if bn == "small":
+                os.environ["SB_TC_SMALL"] = "1"
+                if Co < 128:
+                    continue
+            else:
+                os.environ["SB_TC_SMALL"] = "0"
+                os.environ["SB_TC_BLOCK_N"] = bn
             d = ops.conv_desc(x, w, out, Ci, Co, k, k, 1, k // 2, H, W, scale=sc, shift=sh, residual=r, relu=True)
             for _ in range(3):
                 ops.conv2d(d, "tc")
@@ -73,7 +82,7 @@ def main():
             torch.cuda.synchronize()
             us = s.elapsed_time(e) * 1e3 / reps
             fl = 2.0 * N * H * W * Ci * Co * k * k
-            line += "  BN%s %8.1f us %7.1f TF/s" % (bn, us, fl / us / 1e6)
+            line += "  %s %7.1f us %6.1f TF" % (bn, us, fl / us / 1e6)
         print(line)
 
 
