@@ -243,19 +243,28 @@ __device__ __forceinline__ float coarse_depth(float z0, int h) {
     float d = __fadd_rn(__fsub_rn(z0, 12.5f), (float)(0.5 * h));
     return d < 1.5f ? 1.5f : d;
 }
+// one warp: lane h sums the slices' partials of hypotheses h and h+32 (fixed slice order), then a shuffle
+// argmin with first-index tie break; every lane returns the result
 __device__ __forceinline__ int argmin_partials(const float* __restrict__ part, int nslices, int nh, int row,
                                                float* npix) {
-    int bi = 0;
-    float bc = 0.f;
-    for (int h = 0; h < nh; ++h) {
+    const int lane = threadIdx.x & 31;
+    float best = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int h = lane; h < nh; h += 32) {
         float c = 0.f;
         for (int s = 0; s < nslices; ++s) c += __ldcg(part + (size_t)s * row + h);
-        if (h == 0 || c < bc) { bc = c; bi = h; }
+        if (c < best) { best = c; bi = h; }       // h ascending per lane: first minimum wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
     if (npix) {
         float c = 0.f;
-        for (int s = 0; s < nslices; ++s) c += __ldcg(part + (size_t)s * row + nh);
-        *npix = c;
+        for (int s = lane; s < nslices; s += 32) c += __ldcg(part + (size_t)s * row + nh);
+        *npix = warp_sum(c);
     }
     return bi;
 }
@@ -271,12 +280,16 @@ dense_stage_kernel(const float4* __restrict__ upL, const float4* __restrict__ up
     __shared__ float rdis[50];
     __shared__ float red[8 * 51];
     __shared__ float best_depth;
+    __shared__ int best_idx;
     const int i = blockIdx.x, S = gridDim.y;
-    if (threadIdx.x == 0) {
-        setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
-        if (STAGE == 1) best_depth = coarse_depth(g.z0, argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, nullptr));
+    if (threadIdx.x == 0) setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
+    if (STAGE == 1 && threadIdx.x >= 32 && threadIdx.x < 64) {      // warp 1, concurrently with the box setup
+        const int bi = argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, nullptr);
+        if (threadIdx.x == 32) best_idx = bi;
     }
     __syncthreads();
+    if (STAGE == 1 && threadIdx.x == 0) best_depth = coarse_depth(g.z0, best_idx);
+    if (STAGE == 1) __syncthreads();
     constexpr int NH = STAGE == 0 ? 50 : 20;
     if (threadIdx.x < NH) {
         // fine: depth_j = (best - 0.5) + 0.05 j (dense_align.py:290-294)
@@ -289,7 +302,7 @@ dense_stage_kernel(const float4* __restrict__ upL, const float4* __restrict__ up
     stage_costs<NH>(g, k, upL, upR, rdis, red, blockIdx.y, S, part);
 }
 
-// one CTA: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere -> dis_init" early-out
+// one CTA, one warp per RoI: argmins, outputs, and the reference's "no valid pixel anywhere -> dis_init" early-out
 __global__ void __launch_bounds__(256)
 dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __restrict__ part0,
                    const float* __restrict__ part1, int D, int S, float* __restrict__ status,
@@ -297,16 +310,19 @@ dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __res
     __shared__ int any_valid;
     if (threadIdx.x == 0) any_valid = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < D; i += nw) {
         const float dis_init = __fdiv_rn(k.fb32, poses[7 * i + 2]);
         const float z0 = __fmul_rn(__fmul_rn(__fdiv_rn(1.0f, dis_init), k.f32), k.bl32);
         float npix;
         const float bd0 = coarse_depth(z0, argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, &npix));
         const int bj = argmin_partials(part1 + (size_t)i * S * 21, S, 20, 21, nullptr);
-        const float bd = __fadd_rn(__fsub_rn(bd0, 0.5f), (float)(0.05 * bj));
-        status[i] = npix > 0.f ? 1.f : 0.f;
-        best_dis[i] = __fadd_rn(__fdiv_rn(k.fb32, __fmul_rn(bd, k.s2f)), 0.5f);
-        if (npix > 0.f) any_valid = 1;
+        if (lane == 0) {
+            const float bd = __fadd_rn(__fsub_rn(bd0, 0.5f), (float)(0.05 * bj));
+            status[i] = npix > 0.f ? 1.f : 0.f;
+            best_dis[i] = __fadd_rn(__fdiv_rn(k.fb32, __fmul_rn(bd, k.s2f)), 0.5f);
+            if (npix > 0.f) any_valid = 1;
+        }
     }
     __syncthreads();
     if (!any_valid) {   // dense_align.py:272-273

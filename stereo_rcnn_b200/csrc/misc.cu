@@ -282,8 +282,8 @@ test_decode_kernel(const float* __restrict__ rois_l, const float* __restrict__ r
 }
 
 
-// per-class detection NMS of test_net.py:233-259 in one CTA (R <= 512): threshold, sort by score
-// (desc, index asc), bitmask NMS, greedy scan; keep[] = RoI indices in kept order.
+// per-class detection NMS of test_net.py:233-259 in one CTA (R <= 512): threshold, rank sort by score
+// (desc, index asc), bitmask NMS, survivor-to-survivor greedy scan; keep[] = RoI indices in kept order.
 __global__ void __launch_bounds__(512)
 class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes, int R, int nc, int cls,
                  float score_thresh, float nms_thresh, int* __restrict__ keep, int* __restrict__ num) {
@@ -305,16 +305,14 @@ class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ box
     keys[t] = k;
     __syncthreads();
     if (k) atomicAdd(&n_valid, 1);
-    for (int kk = 2; kk <= 512; kk <<= 1)
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            const int ixj = t ^ j;
-            if (ixj > t) {
-                const unsigned long long a = keys[t], b = keys[ixj];
-                const bool desc = (t & kk) == 0;
-                if (desc ? (a < b) : (a > b)) { keys[t] = b; keys[ixj] = a; }
-            }
-            __syncthreads();
-        }
+    {   // rank sort (keys unique; zeros = below threshold rank last): 512 broadcast compares per thread
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 512; ++j) rank += keys[j] > k;
+        __syncthreads();
+        if (k) keys[rank] = k;
+        __syncthreads();
+    }
     const int n = n_valid;
     if (t < n) {
         const int idx = (int)(0xFFFFFFFFu - (unsigned)(keys[t] & 0xFFFFFFFFu));
@@ -334,13 +332,20 @@ class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ box
         }
     }
     __syncthreads();
-    if (t == 0) {
+    if (t == 0) {   // greedy scan jumping from survivor to survivor
         unsigned long long remv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int cnt = 0;
-        for (int i = 0; i < n; ++i) {
-            if (!((remv[i >> 6] >> (i & 63)) & 1ULL)) {
+        for (int w = 0; w < words; ++w) {
+            const int cs = min(n - w * 64, 64);
+            const unsigned long long valid = cs >= 64 ? ~0ULL : ((1ULL << cs) - 1ULL);
+            unsigned long long avail = ~remv[w] & valid;
+            while (avail) {
+                const int b = __ffsll((long long)avail) - 1;
+                const int i = w * 64 + b;
                 keep[cnt++] = (int)(0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFu));
-                for (int w = i >> 6; w < words; ++w) remv[w] |= mask[i][w];
+                for (int w2 = w; w2 < words; ++w2) remv[w2] |= mask[i][w2];
+                const unsigned long long above = b >= 63 ? 0ULL : (~0ULL << (b + 1));
+                avail = ~remv[w] & valid & above;
             }
         }
         *num = cnt;

@@ -9,7 +9,7 @@
 //   1. 3-pass radix select of the pre_nms_top_n-th largest score (11+11+10 bits)
 //   2. ordered compaction of the survivors (ties broken by ascending anchor index --
 //      the total order the oracle pins; the reference leaves ties to torch.sort)
-//   3. single-CTA bitonic sort of <= 16384 (score, index) keys in shared memory
+//   3. rank sort of the <= 16384 unique (score, index) keys (K^2 compare-adds over K/64 CTAs)
 //   4. anchors generated in fp64 *for survivors only* (bit-equal to the numpy table),
 //      left/right decode + clip with the shared deterministic expf
 //   5. upper-triangle bitmask NMS for both sides in one launch + lock-step greedy
@@ -226,30 +226,27 @@ compact_kernel(const float* __restrict__ prob, int A, const SelState* __restrict
     }
 }
 
-// single-CTA bitonic sort (descending) of Kpad keys in dynamic shared memory
-__global__ void __launch_bounds__(1024)
-sort_kernel(unsigned long long* __restrict__ cand, int K, int Kpad, int* __restrict__ order,
-            float* __restrict__ score) {
-    extern __shared__ unsigned long long sk[];
-    for (int i = threadIdx.x; i < Kpad; i += 1024) sk[i] = i < K ? cand[i] : 0ULL;
-    __syncthreads();
-    for (int k = 2; k <= Kpad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < Kpad; i += 1024) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = sk[i], b = sk[ixj];
-                    bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) { sk[i] = b; sk[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
+// Rank sort of the K unique 64-bit keys (descending): rank(i) = #{j : key_j > key_i}.  K^2 = 36 M
+// compare-adds spread over ceil(K/64) CTAs replace the 91 barrier-separated steps of a single-CTA bitonic
+// sort (13 us instead of 105 us at K = 6000); keys are streamed through shared memory as broadcast reads.
+__global__ void __launch_bounds__(64)
+rank_sort_kernel(const unsigned long long* __restrict__ cand, int K, int* __restrict__ order,
+                 float* __restrict__ score) {
+    __shared__ unsigned long long tile[1024];
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    const unsigned long long my = i < K ? cand[i] : ~0ULL;
+    int rank = 0;
+    for (int base = 0; base < K; base += 1024) {
+        const int cnt = min(1024, K - base);
+        for (int j = threadIdx.x; j < cnt; j += 64) tile[j] = cand[base + j];
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < cnt; ++j) rank += tile[j] > my;
+        __syncthreads();
     }
-    for (int i = threadIdx.x; i < K; i += 1024) {
-        unsigned long long k64 = sk[i];
-        order[i] = (int)(0xFFFFFFFFu - (unsigned)(k64 & 0xFFFFFFFFu));
-        score[i] = key_to_float((unsigned)(k64 >> 32));
+    if (i < K) {
+        order[rank] = (int)(0xFFFFFFFFu - (unsigned)(my & 0xFFFFFFFFu));
+        score[rank] = key_to_float((unsigned)(my >> 32));
     }
 }
 
@@ -403,11 +400,6 @@ extern "C" int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_l
     int* num = (int*)(ws + w.num);
     const int nblocks = (A + kChunk - 1) / kChunk;
     int Kpad = 1; while (Kpad < K) Kpad <<= 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-        attr_set = true;
-    }
     for (int b = 0; b < B; ++b) {
         const float* prob = cls_prob + (size_t)b * A * 2;
         const float* deltas = bbox_pred_lr + (size_t)b * A * 6;
@@ -420,7 +412,7 @@ extern "C" int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_l
         count_eq_kernel<<<nblocks, 256, 0, st>>>(prob, A, state, block_eq, block_gt); SB_LAUNCHED();
         block_scan_kernel<<<1, 1024, 0, st>>>(block_eq, block_gt, nblocks, state); SB_LAUNCHED();
         compact_kernel<<<nblocks, 256, 0, st>>>(prob, A, state, block_eq, block_gt, cand, K); SB_LAUNCHED();
-        sort_kernel<<<1, 1024, (size_t)Kpad * 8, st>>>(cand, K, Kpad, order, score); SB_LAUNCHED();
+        rank_sort_kernel<<<(K + 63) / 64, 64, 0, st>>>(cand, K, order, score); SB_LAUNCHED();
         decode_kernel<<<(K + 255) / 256, 256, 0, st>>>(order, K, deltas, im_info + 3 * b, ac, prop_l, prop_r);
         SB_LAUNCHED();
         SB_CHECK_LAUNCH();
