@@ -53,6 +53,7 @@ class StereoRCNNEngine(object):
         self.n_classes = n_classes
         self.conv_impl = conv_impl
         self.impl_used = {}
+        self.record = None        # bench: list collecting (desc, live tensors) of every conv launch of a forward
         # conv_impl="simt" is the exact-fp32 yardstick: exact weights, exact stores, no TF32 hygiene modes
         self.exact = conv_impl == "simt"
         PackedConv.round_weights = not self.exact
@@ -137,6 +138,8 @@ class StereoRCNNEngine(object):
                           up_src=up_src, relu=relu, out_coff=out_coff, out_strides=out_strides, out_mode=out_mode,
                           res_biased=res_biased, in_biased=in_biased, out16=out16)
         impl = ops.conv2d(d, "tc" if half_in else self.conv_impl)
+        if self.record is not None:
+            self.record.append((d, impl, (x, out, out16, residual, up_src)))
         if tag is not None:
             self.impl_used[tag] = impl + ("16" if half_in else "")
         if out is not None and out16 is not None:
