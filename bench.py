@@ -97,24 +97,27 @@ class Pipeline(object):
         self.ops, self.dev = ops, device
         self.eng = engine.StereoRCNNEngine(make_state_dict(3), device)
         self.info = torch.tensor([[H_NET, W_NET, SCALE]], dtype=torch.float32, device=device)
-        self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "0") != "0" else None
+        self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "1") != "0" else None
 
     def step(self, iml, imr, calib4, rois3d):
         ops = self.ops
-        if self.side is not None:
-            # dense_align depends only on the input pair: fork it onto a second stream (a parallel branch of the
-            # CUDA graph) so that its 2 launches fill SMs the persistent conv CTAs leave idle at their tails
+        side_out = []
+
+        def fork_dense_align():
+            # dense_align depends only on the input pair and the (synthetic) poses: a parallel branch of the CUDA
+            # graph, forked where the main branch runs its small proposal kernels and most SMs are idle
             main = torch.cuda.current_stream()
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
-                st, dis = ops.dense_align(calib4, SCALE32, iml, imr, *rois3d)
-        o = self.eng.forward(iml, imr, self.info)
+                side_out.extend(ops.dense_align(calib4, SCALE32, iml, imr, *rois3d))
+        o = self.eng.forward(iml, imr, self.info, before_proposals=fork_dense_align if self.side is not None else None)
         pbl, pbr, dimo, pk = ops.test_decode(o["rois_left"][0], o["rois_right"][0], o["bbox_pred"][0],
                                              o["dim_orien_pred"][0], o["kpts_prob"], o["left_border_prob"],
                                              o["right_border_prob"], self.info[0])
         keep, nkeep = ops.class_nms(o["cls_prob"][0], pbl, 1, 0.05, 0.3)
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
+            st, dis = side_out
         else:
             st, dis = ops.dense_align(calib4, SCALE32, iml, imr, *rois3d)
         rec = self.par.detection_record(o["cls_prob"][0], pbl, pbr, dimo, pk)   # [300, 33]

@@ -136,7 +136,9 @@ typedef struct {
      * (in_dtype 1, Cin % 64 == 0); out16, when non-NULL, receives an fp16 (round-to-nearest) twin of the
      * output with the same element strides; out may be NULL when only the fp16 twin is wanted.          */
     void* out16;
-    int in_dtype, reserved0;
+    int in_dtype;
+    int max_ctas;           /* 0 = one persistent CTA per SM; otherwise cap the grid (concurrent launches on
+                             * other streams get the remaining SMs) */
 } sb_conv_desc;
 
 int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream);

@@ -540,7 +540,8 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
         if (num_sms <= 0) num_sms = 148;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int slots = num_sms * (EW == 4 ? 2 : 1);
+    int slots = num_sms * (EW == 4 ? 2 : 1);
+    if (p.d.max_ctas > 0 && p.d.max_ctas < slots) slots = p.d.max_ctas;
     const int grid = tiles < slots ? tiles : slots;
     static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};

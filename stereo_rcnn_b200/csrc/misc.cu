@@ -321,15 +321,14 @@ class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ box
     }
     __syncthreads();
     const int words = (n + 63) >> 6;
-    if (t < n) {
-        const float4 cur = sbox[t];
-        for (int w = 0; w < words; ++w) {
-            unsigned long long bits = 0;
-            const int j0 = w * 64, j1 = min(n, j0 + 64);
-            for (int j = max(j0, t + 1); j < j1; ++j)
-                if (sb_iou_gt(cur, sbox[j], nms_thresh)) bits |= 1ULL << (j - j0);
-            mask[t][w] = bits;
-        }
+    for (int item = t; item < n * words; item += 512) {      // one (row, 64-box word) pair per work item
+        const int row = item / words, w = item - row * words;
+        const float4 cur = sbox[row];
+        unsigned long long bits = 0;
+        const int j0 = w * 64, j1 = min(n, j0 + 64);
+        for (int j = max(j0, row + 1); j < j1; ++j)
+            if (sb_iou_gt(cur, sbox[j], nms_thresh)) bits |= 1ULL << (j - j0);
+        mask[row][w] = bits;
     }
     __syncthreads();
     if (t == 0) {   // greedy scan jumping from survivor to survivor

@@ -60,7 +60,6 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask0,
                   const unsigned long long* __restrict__ mask1, int n, int max_out,
                   int* __restrict__ keep_out, int* __restrict__ num_out) {
     __shared__ unsigned long long remv[NS][kMaxWords];
-    __shared__ unsigned long long diag[NS][kTile];
     __shared__ unsigned long long keepbits[NS];
     __shared__ int count;
     const int side = threadIdx.x >> 8, t = threadIdx.x & 255;
@@ -71,17 +70,27 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask0,
     __syncthreads();
     for (int c = 0; c < cb; ++c) {
         const int csize = min(n - c * kTile, kTile);
-        if (t < kTile) diag[side][t] = (t < csize) ? mask[(size_t)(c * kTile + t) * cb + c] : 0ULL;
-        __syncthreads();
-        if (t == 0) {
+        // resolve the chunk's 64x64 diagonal tile inside warp 0 of each side: lane l holds rows l and l+32 in
+        // registers and the sequential scan broadcasts row b with a shuffle (no shared-memory latency on the
+        // 64-step dependency chain)
+        if (t < 32) {
+            const int r0 = c * kTile + t, r1 = r0 + 32;
+            const unsigned long long d0 = (t < csize) ? mask[(size_t)r0 * cb + c] : 0ULL;
+            const unsigned long long d1 = (t + 32 < csize) ? mask[(size_t)r1 * cb + c] : 0ULL;
             unsigned long long cur = remv[side][c], kb = 0;
-            for (int b = 0; b < csize; ++b) {
-                if (!((cur >> b) & 1ULL)) {
-                    kb |= 1ULL << b;
-                    cur |= diag[side][b];
-                }
+            const unsigned long long valid = csize >= 64 ? ~0ULL : ((1ULL << csize) - 1ULL);
+            cur |= ~valid;
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const unsigned long long row = __shfl_sync(0xffffffffu, d0, b);
+                if (!((cur >> b) & 1ULL)) { kb |= 1ULL << b; cur |= row; }
             }
-            keepbits[side] = kb;
+#pragma unroll 8
+            for (int b = 0; b < 32; ++b) {
+                const unsigned long long row = __shfl_sync(0xffffffffu, d1, b);
+                if (!((cur >> (b + 32)) & 1ULL)) { kb |= 1ULL << (b + 32); cur |= row; }
+            }
+            if (t == 0) keepbits[side] = kb;
         }
         __syncthreads();
         if (threadIdx.x == 0) {

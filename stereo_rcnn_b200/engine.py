@@ -49,10 +49,14 @@ class StereoRCNNEngine(object):
         self.half = precision == "fp16" and conv_impl != "simt"
         self.precision = "fp32-simt" if conv_impl == "simt" else precision
         self.keep32 = False
+        self.chain_ctas = int(os.environ.get("SB_CHAIN_CTAS", "0"))
+        self.side = (torch.cuda.Stream(device=torch.device(device)) if os.environ.get("SB_LR_STREAMS", "1") != "0"
+                     and torch.device(device).type == "cuda" else None)
         self.device = torch.device(device)
         self.n_classes = n_classes
         self.conv_impl = conv_impl
         self.impl_used = {}
+        self.max_ctas = 0         # grid cap for convs issued while a second chain runs on the side stream
         self.record = None        # bench: list collecting (desc, live tensors) of every conv launch of a forward
         # conv_impl="simt" is the exact-fp32 yardstick: exact weights, exact stores, no TF32 hygiene modes
         self.exact = conv_impl == "simt"
@@ -136,7 +140,7 @@ class StereoRCNNEngine(object):
         d = ops.conv_desc(x, pc.w16 if half_in else pc.w, out, pc.Cin if Cin is None else Cin, pc.Cout, pc.kh,
                           pc.kw, stride, pc.pad, Ho, Wo, scale=pc.scale, shift=pc.shift, residual=residual,
                           up_src=up_src, relu=relu, out_coff=out_coff, out_strides=out_strides, out_mode=out_mode,
-                          res_biased=res_biased, in_biased=in_biased, out16=out16)
+                          res_biased=res_biased, in_biased=in_biased, out16=out16, max_ctas=self.max_ctas)
         impl = ops.conv2d(d, "tc" if half_in else self.conv_impl)
         if self.record is not None:
             self.record.append((d, impl, (x, out, out16, residual, up_src)))
@@ -162,12 +166,16 @@ class StereoRCNNEngine(object):
         return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3",
                           out_mode=ops.BIASED, res_biased=not has_ds)
 
-    def _bottleneck16(self, x32, x16, prefix, stride, has_ds):
-        """fp16-operand variant: convs read fp16 twins, the residual stream itself stays exact fp32"""
+    def _bottleneck16(self, x32, x16, prefix, stride, has_ds, out=None):
+        """fp16-operand variant: convs read fp16 twins, the residual stream itself stays exact fp32.
+        out = (fp32 view, fp16 view) to write the block output into (slices of a batched tensor)"""
         xin = ops.subsample2(x16) if stride == 2 else x16
         o = self._conv(xin, self.p[prefix + ".conv1"], relu=True, tag=prefix + ".conv1", f32=False, f16=True)
         o = self._conv(o, self.p[prefix + ".conv2"], relu=True, tag=prefix + ".conv2", f32=False, f16=True)
         res = self._conv(xin, self.p[prefix + ".downsample.0"], tag=prefix + ".ds") if has_ds else x32
+        if out is not None:
+            return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3",
+                              out=out[0], out16=out[1])
         return self._conv(o, self.p[prefix + ".conv3"], relu=True, residual=res, tag=prefix + ".conv3", f16=True)
 
     def trunk_fpn(self, im_nchw):
@@ -205,11 +213,49 @@ class StereoRCNNEngine(object):
         c1 = ops.maxpool3x3s2_ceil(c0)
         feats = {"c1": c1.float() if self.keep32 else None, "c1_16": c1}
         x32, x16 = None, c1
-        for li, nb in enumerate(LAYERS):
-            for bi in range(nb):
+        for li in (0, 1):                           # layers 1-2: left and right batched (hundreds of tiles)
+            for bi in range(LAYERS[li]):
                 x32, x16 = self._bottleneck16(x32, x16, "RCNN_layer%d.0.%d" % (li + 1, bi),
                                               STRIDES[li] if bi == 0 else 1, bi == 0)
             feats["c%d" % (li + 2)], feats["c%d_16" % (li + 2)] = x32, x16
+        # layers 3-4 have 38 / 10 row tiles per image: far too few to fill 148 SMs, and every launch is latency
+        # bound (prologue + load latency + main loop + epilogue back to back).  The left and the right image are
+        # independent, so they run as two concurrent chains on two streams (two parallel branches of the CUDA
+        # graph): the chains' latencies overlap and together they still need only ~76 SMs.
+        N = x16.shape[0]
+        B = N // 2
+        dev = x16.device
+
+        def out_bufs(li):
+            h, w = x16.shape[1], x16.shape[2]
+            for _ in range(li - 1):
+                h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            c = PLANES[li] * 4
+            return (torch.empty(N, h, w, c, dtype=torch.float32, device=dev),
+                    torch.empty(N, h, w, c, dtype=torch.float16, device=dev))
+        c4 = out_bufs(2)
+        c5 = out_bufs(3)
+
+        def chain(sl):
+            y32, y16 = x32[sl], x16[sl]
+            for li, dst in ((2, c4), (3, c5)):
+                for bi in range(LAYERS[li]):
+                    last = bi == LAYERS[li] - 1
+                    y32, y16 = self._bottleneck16(y32, y16, "RCNN_layer%d.0.%d" % (li + 1, bi),
+                                                  STRIDES[li] if bi == 0 else 1, bi == 0,
+                                                  out=(dst[0][sl], dst[1][sl]) if last else None)
+        if self.side is not None:
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            self.max_ctas = self.chain_ctas      # each chain keeps to half of the SMs so that both really co-run
+            with torch.cuda.stream(self.side):
+                chain(slice(B, N))
+            chain(slice(0, B))
+            self.max_ctas = 0
+            main.wait_stream(self.side)
+        else:
+            chain(slice(0, N))
+        feats.update(c4=c4[0], c4_16=c4[1], c5=c5[0], c5_16=c5[1])
         p5, p5h = self._conv(feats["c5_16"], self.p["RCNN_toplayer"], tag="toplayer", f16=True)
         t = self._conv(feats["c4_16"], self.p["RCNN_latlayer1"], up_src=p5, tag="lat1", f32=False, f16=True)
         p4, p4h = self._conv(t, self.p["RCNN_smooth1"], tag="smooth1", f16=True)
@@ -280,7 +326,8 @@ class StereoRCNNEngine(object):
                     kpts_pred_all=ka)
 
     @torch.no_grad()
-    def forward(self, im_left, im_right, im_info, cfg_key="TEST", keep_features=False, im_h=None):
+    def forward(self, im_left, im_right, im_info, cfg_key="TEST", keep_features=False, im_h=None,
+                before_proposals=None):
         """im_left/right [B,3,H,W] NCHW fp32 (BGR - means), im_info [B,3] (device) -> dict (the reference's
         tuple order is produced by model.stereo_rcnn.resnet.resnet.forward).  `im_h` (= im_info[0][0],
         stereo_rcnn.py:128) is taken from the tensor shape so that no device->host read is needed."""
@@ -289,6 +336,10 @@ class StereoRCNNEngine(object):
         im = torch.cat((im_left, im_right), 0).contiguous()
         feats = self.trunk_fpn(im)
         cls_prob, bbox, shapes = self.rpn(feats, B)
+        if before_proposals is not None:
+            # the proposal stage is a chain of small, partly single-CTA kernels: callers fork independent work
+            # (e.g. dense_align of the previous detections) onto a second stream here so that it fills the idle SMs
+            before_proposals()
         rl, rr = ops.proposal_layer(cls_prob, bbox, im_info, cfg_key, shapes)
         out = self.heads(feats, B, rl.view(-1, 5), rr.view(-1, 5), im_h)
         n = rl.shape[1]

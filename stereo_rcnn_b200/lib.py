@@ -32,7 +32,7 @@ class ConvDesc(ctypes.Structure):
                 ("in_ld", c_int), ("res_ld", c_int), ("UH", c_int), ("UW", c_int), ("relu", c_int),
                 ("out_coff", c_int), ("out_mode", c_int), ("res_biased", c_int), ("in_biased", c_int),
                 ("out_n_stride", c_ll), ("out_h_stride", c_ll), ("out_w_stride", c_ll),
-                ("out16", c_void_p), ("in_dtype", c_int), ("reserved0", c_int)]
+                ("out16", c_void_p), ("in_dtype", c_int), ("max_ctas", c_int)]
 
 
 _SIGS = {

@@ -191,7 +191,7 @@ def dense_align(calib4, scale, im_left, im_right, box_left, keypoints, poses):
 # ------------------------------------------------------------- layer ops ----
 def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, shift=None, residual=None,
               up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None, out_mode=0, res_biased=False,
-              in_biased=False, out16=None):
+              in_biased=False, out16=None, max_ctas=0):
     """x: NHWC [N,H,W,in_ld]; wgt packed [Cout,kh,kw,Cin]; out: any tensor addressed through out_strides
     = (n, h, w) strides in floats (default: dense NHWC of out.shape[-1] channels)."""
     d = ConvDesc()
@@ -200,6 +200,7 @@ def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, s
     d.out = out.data_ptr() if out is not None else None
     d.out16 = out16.data_ptr() if out16 is not None else None
     d.in_dtype = 1 if x.dtype == torch.float16 else 0
+    d.max_ctas = int(max_ctas)
     assert wgt.dtype == x.dtype, "weights and activations of a conv share one operand type"
     d.scale = scale.data_ptr() if scale is not None else None
     d.shift = shift.data_ptr() if shift is not None else None
