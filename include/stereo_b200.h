@@ -146,6 +146,14 @@ int sb_conv2d_simt(const sb_conv_desc* d, sb_stream_t stream);
 int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream);
 int sb_conv2d_tc_supported(const sb_conv_desc* d);
 
+/* Diagnostics (tools/conv_trace.py): per-CTA phase timestamps of every following sb_conv2d_tc launch, 16 x u64
+ * per CTA and 304 CTA slots per launch, into a caller-owned device buffer of sb_conv_trace_bytes(max_launches)
+ * bytes.  buf = NULL switches tracing off.  No counterpart in the reference. */
+size_t sb_conv_trace_bytes(int max_launches);
+int sb_conv_trace(void* buf, int max_launches);
+int sb_conv_trace_count(void);
+int sb_conv_trace_info(int id, int* out12);
+
 /* stem: NCHW image -> conv7x7/2 + frozen BN + ReLU -> NHWC (resnet.py:111-113) */
 int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[64][7][7][3]*/,
                  const float* scale, const float* shift, float* out_nhwc, int out_mode, sb_stream_t stream);

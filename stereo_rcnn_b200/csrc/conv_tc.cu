@@ -160,7 +160,7 @@ struct RowInfo {          // per accumulator row of the current tile (one per la
     int pad;
 };
 
-constexpr size_t epi_smem(int ew) { return (size_t)ew * (32 * 8 * 16 + 32 * sizeof(RowInfo)); }
+constexpr size_t epi_smem(int ew) { return (size_t)ew * (32 * 8 * 16); }
 
 struct TcParams {
     sb_conv_desc d;
@@ -170,7 +170,16 @@ struct TcParams {
     int kblocks_per_tap;  // Cin / 32
     int num_k_blocks;     // taps * kblocks_per_tap
     long long M;
+    int pdl_late;         // fire griddepcontrol.launch_dependents after the last tile's MMAs instead of at entry
+    unsigned long long* trace;   // optional per-CTA phase timestamps (sb_conv_trace), 16 words per CTA
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int kTraceWords = 16, kTraceCtas = 304;
 
 template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
@@ -188,14 +197,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tfull = empty + kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [Cout rounded up to BLOCK_N]
-    float* s_shift = s_scale + kMaxCout;
-    float4* epi_stage = reinterpret_cast<float4*>(s_shift + kMaxCout);            // [8 warps][32 rows][8 float4]
-    RowInfo* epi_rows = reinterpret_cast<RowInfo*>(epi_stage + EW * 32 * 8);   // [EW warps][32]
-    constexpr int kNumThreads = 64 + 32 * EW;
+    float4* epi_stage = reinterpret_cast<float4*>(smem + kStages * kStageBytes + 256);   // [EW warps][32 rows][8 float4]
+    static_assert((2 * kStages + 4) * 8 + 16 <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const sb_conv_desc& d = p.d;
+    unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * kTraceWords : nullptr;
+    if (tr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = gtimer(); tr[8] = clock64(); tr[6] = smid;
+    }
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&map_a);
@@ -212,13 +224,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    {   // folded-BN scale / shift (or bias) for every output channel, once per (persistent) CTA
-        const int cpad = p.num_n_tiles * BLOCK_N;
-        for (int c = threadIdx.x; c < cpad; c += kNumThreads) {
-            s_scale[c] = (d.scale && c < d.Cout) ? d.scale[c] : 1.f;
-            s_shift[c] = (d.shift && c < d.Cout) ? d.shift[c] : 0.f;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -226,8 +231,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch,
     // scale/shift staging -- weights only) overlapped the previous kernel's tail.  Let the next kernel start
     // its own prologue as soon as our CTAs retire, then wait for the producers of our activations.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tr && threadIdx.x == 0) { tr[1] = gtimer(); tr[9] = clock64(); }
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
@@ -278,6 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
+                if (tr && lane == 0 && kb == 0 && tile == (int)blockIdx.x) { tr[2] = gtimer(); tr[10] = clock64(); }
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
@@ -295,22 +302,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (tr && lane == 0) { tr[3] = gtimer(); tr[11] = clock64(); }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         // warp w may only touch TMEM lanes 32*(w%4)..+31; two warps share each lane quarter and split the
         // tile's columns in halves.  Per 32-column chunk: TMEM -> registers (one accumulator row per thread)
-        // -> scale/shift (one FFMA) -> XOR-swizzled per-warp staging tile in shared memory -> read back
-        // transposed so that every global access of the warp covers four full 128-byte rows.  The epilogue
-        // is instruction-issue bound (ncu: ~2 warp-instructions per output element before this rewrite), so
-        // row addressing is hoisted to once per tile and the residual / upsample paths are compile-time.
+        // -> XOR-swizzled per-warp staging tile in shared memory -> read back transposed, so that every global
+        // access of the warp covers four full 128-byte rows and each lane owns four fixed channels: scale /
+        // shift are two register float4 per chunk.  The epilogue is latency / issue bound, so row addressing
+        // is hoisted to once per tile (exchanged through the idle staging tile: shared memory is spent on
+        // operand stages, the main loop being bound by bytes in flight), the residual rows are prefetched two
+        // chunks ahead -- across tile boundaries -- and the bilinear taps of the FPN upsample-add are issued
+        // four rows at a time before they are consumed.
         const int q = warp & 3;
         const int ew = warp - 2;
         const int half = EW == 8 ? (ew >> 2) : 0;
         constexpr int kColsPerWarp = EW == 8 ? (BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32) : BLOCK_N;
+        constexpr int kChunks = kColsPerWarp / 32;
         const int col_begin = half * kColsPerWarp;
         const bool has_cols = col_begin < BLOCK_N;
         float4* stg = epi_stage + ew * (32 * 8);
-        RowInfo* ri = epi_rows + ew * 32;
+        RowInfo* ri = reinterpret_cast<RowInfo*>(stg);      // 32 * sizeof(RowInfo) <= the 4 KB staging tile
+        static_assert(32 * sizeof(RowInfo) <= 32 * 8 * sizeof(float4), "row exchange fits the staging tile");
         int acc = 0;
         uint32_t acc_phase = 0;
         float rh = 0.f, rw = 0.f;
@@ -322,8 +336,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const bool relu = d.relu != 0;
         const int out_mode = d.out_mode;
         const bool res_biased = d.res_biased != 0;
+        // residual rows (HAS_RES implies a 1x1 conv, i.e. flat rows: row m of the output is row m of the residual)
+        float4 r4[2][8];
+        const float* rbase = nullptr;     // residual row of this lane's first row (rows 4*i+rsub are 4*res_ld apart)
+        int rrows = 0;                    // how many of the lane's 8 rows exist (m < M)
+        const long long rstep = 4ll * d.res_ld;
+        bool prefetched = false;      // r4 already holds the first chunks of the tile about to be processed
+        auto res_rows = [&](int mt_) {
+            const long long m0 = (long long)mt_ * BLOCK_M + q * 32 + rsub;
+            const long long left = p.M - m0;                     // rows m0, m0+4, ... < M
+            rrows = left <= 0 ? 0 : (left >= 32 ? 8 : (int)((left + 3) >> 2));
+            rbase = d.residual + (left <= 0 ? 0 : m0) * d.res_ld + 4 * c4;
+        };
+        auto load_res = [&](int buf, int cbase) {
+            const int live = (cbase + 4 * c4 < d.Cout) ? rrows : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                r4[buf][i] = (i < live) ? __ldg(reinterpret_cast<const float4*>(rbase + i * rstep + cbase))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+            unsigned ooff[8];          // element offsets < 2^31 (checked on the host)
+            unsigned vmask = 0;
+            int uoff[8];
+            float uly[8], ulx[8];
+            unsigned fy = 0, fx = 0;
             {   // this lane describes accumulator row q*32+lane of the tile
                 const int row = q * 32 + lane;
                 int n_img, ho, wo;
@@ -348,10 +386,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 RowInfo inf;
                 inf.out_off = (long long)n_img * d.out_n_stride + (long long)ho * d.out_h_stride +
                               (long long)wo * d.out_w_stride + d.out_coff;
-                inf.res_off = ((long long)(n_img * d.Ho + ho) * d.Wo + wo) * d.res_ld;
+                inf.res_off = 0;
                 inf.flags = valid ? 1 : 0;
                 inf.up_off = 0; inf.ly1 = 0.f; inf.lx1 = 0.f;
-                if (HAS_UP) {
+                if (HAS_UP && valid) {
                     const float sy = __fmul_rn(rh, (float)ho), sx = __fmul_rn(rw, (float)wo);
                     const int y1 = (int)sy, x1 = (int)sx;
                     if (y1 < d.UH - 1) inf.flags |= 2;
@@ -360,37 +398,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     inf.lx1 = sx - (float)x1;
                     inf.up_off = (((long long)n_img * d.UH + y1) * d.UW + x1) * d.Cout;
                 }
-                __syncwarp();
+                __syncwarp();           // the previous tile's staging reads are done
                 ri[lane] = inf;
                 __syncwarp();
-            }
-            // rows this lane touches in the coalesced domain: 4*i + rsub, i = 0..7
-            long long ooff[8];
-            const float* rptr[8];
-            unsigned vmask = 0;
+                // rows this lane touches in the coalesced domain: 4*i + rsub, i = 0..7
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const RowInfo& inf = ri[4 * i + rsub];
-                ooff[i] = inf.out_off + 4 * c4;
-                rptr[i] = HAS_RES ? d.residual + inf.res_off + 4 * c4 : nullptr;
-                vmask |= (unsigned)(inf.flags & 1) << i;
+                for (int i = 0; i < 8; ++i) {
+                    const RowInfo& o = ri[4 * i + rsub];
+                    ooff[i] = (unsigned)o.out_off + 4u * c4;
+                    vmask |= (unsigned)(o.flags & 1) << i;
+                    if (HAS_UP) {
+                        uoff[i] = (int)o.up_off;
+                        uly[i] = o.ly1;
+                        ulx[i] = o.lx1;
+                        fy |= (unsigned)((o.flags >> 1) & 1) << i;
+                        fx |= (unsigned)((o.flags >> 2) & 1) << i;
+                    }
+                }
+                __syncwarp();           // staging tile free again
             }
-            // residual rows are fetched into registers two chunks ahead -- the first two before the tile's
-            // accumulator is even complete, so the HBM latency hides behind the MMA main loop
-            constexpr int kChunks = kColsPerWarp / 32;
-            float4 r4[2][8];
             const int cb0 = nt * BLOCK_N + col_begin;
-            auto load_res = [&](int buf, int k) {
-                const int cbase = cb0 + 32 * k;
-                const unsigned live = (cbase + 4 * c4 < d.Cout) ? vmask : 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    r4[buf][i] = ((live >> i) & 1u) ? __ldg(reinterpret_cast<const float4*>(rptr[i] + cbase))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            if (HAS_RES && has_cols) {
-                load_res(0, 0);
-                if (kChunks > 1) load_res(1, 1);
+            if (HAS_RES && has_cols && !prefetched) {
+                // the first tile's residual rows are requested before its accumulator is complete, so their
+                // latency hides behind the MMA main loop
+                res_rows(mt);
+                load_res(0, cb0);
+                if (kChunks > 1) load_res(1, cb0 + 32);
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
@@ -401,48 +434,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc), v);
                     const int cbase = nt * BLOCK_N + cc;
-                    const unsigned live = (cbase + 4 * c4 < d.Cout) ? vmask : 0u;
+                    const int cidx = cbase + 4 * c4;
+                    const bool col_ok = cidx < d.Cout;
+                    const unsigned live = col_ok ? vmask : 0u;
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col_ok) {
+                        if (d.scale) { sc.x = __ldg(d.scale + cidx); sc.y = __ldg(d.scale + cidx + 1); sc.z = __ldg(d.scale + cidx + 2); sc.w = __ldg(d.scale + cidx + 3); }
+                        if (d.shift) { sh.x = __ldg(d.shift + cidx); sh.y = __ldg(d.shift + cidx + 1); sh.z = __ldg(d.shift + cidx + 2); sh.w = __ldg(d.shift + cidx + 3); }
+                    }
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + cbase + 4 * j);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + cbase + 4 * j);
-                        float4 o;
-                        o.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-                        o.y = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-                        o.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-                        o.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-                        stg[lane * 8 + (j ^ (lane & 7))] = o;
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + rsub;
-                        float4 x = stg[r * 8 + (c4 ^ (r & 7))];
-                        if (!((live >> i) & 1u)) continue;
-                        if (HAS_RES) {
-                            float4 rr = r4[k & 1][i];
-                            if (res_biased) {
-                                rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
-                                rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
-                            }
-                            x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-                        }
-                        if (HAS_UP) {
-                            const RowInfo inf = ri[r];
-                            const float* u00 = d.up_src + inf.up_off + cbase + 4 * c4;
-                            const long long dx = (inf.flags & 4) ? d.Cout : 0;
-                            const long long dy = (inf.flags & 2) ? (long long)d.UW * d.Cout : 0;
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(u00));
-                            const float4 bq = __ldg(reinterpret_cast<const float4*>(u00 + dx));
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(u00 + dy));
-                            const float4 h = __ldg(reinterpret_cast<const float4*>(u00 + dy + dx));
-                            const float ly1 = inf.ly1, ly0 = 1.f - ly1, lx1 = inf.lx1, lx0 = 1.f - lx1;
-                            x.x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
-                            x.y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
-                            x.z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
-                            x.w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
-                        }
+                    auto finish = [&](int i, float4 x) {       // relu / store mode / fp32 + fp16 stores of one row quad
                         if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                         if (out_mode == 1) {
                             x.x = sb_round_tf32(x.x); x.y = sb_round_tf32(x.y); x.z = sb_round_tf32(x.z); x.w = sb_round_tf32(x.w);
@@ -458,20 +464,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             pk.y = *reinterpret_cast<uint32_t*>(&hi);
                             *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + cbase) = pk;
                         }
+                    };
+                    auto staged = [&](int i) {                 // accumulator quad of row 4*i+rsub, scale / shift applied
+                        const int r = 4 * i + rsub;
+                        float4 x = stg[r * 8 + (c4 ^ (r & 7))];
+                        x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                        x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+                        return x;
+                    };
+                    if (HAS_UP) {
+                        const float* ubase = d.up_src + (col_ok ? cidx : 0);
+                        const long long ustep_y = (long long)d.UW * d.Cout;
+#pragma unroll
+                        constexpr int UB = 2;                     // rows per batch: 4 * UB independent tap loads in flight
+#pragma unroll
+                        for (int hh = 0; hh < 8 / UB; ++hh) {
+                            float4 ta[UB], tb[UB], tg[UB], th[UB];
+#pragma unroll
+                            for (int ii = 0; ii < UB; ++ii) {
+                                const int i = hh * UB + ii;
+                                const float* u00 = ubase + uoff[i];
+                                const long long dx = ((fx >> i) & 1u) ? d.Cout : 0;
+                                const long long dy = ((fy >> i) & 1u) ? ustep_y : 0;
+                                ta[ii] = __ldg(reinterpret_cast<const float4*>(u00));
+                                tb[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dx));
+                                tg[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dy));
+                                th[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dy + dx));
+                            }
+#pragma unroll
+                            for (int ii = 0; ii < UB; ++ii) {
+                                const int i = hh * UB + ii;
+                                float4 x = staged(i);
+                                if (!((live >> i) & 1u)) continue;
+                                const float4 a = ta[ii], bq = tb[ii], g = tg[ii], h = th[ii];
+                                const float ly1 = uly[i], ly0 = 1.f - ly1, lx1 = ulx[i], lx0 = 1.f - lx1;
+                                x.x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
+                                x.y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
+                                x.z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
+                                x.w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
+                                finish(i, x);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 x = staged(i);
+                            if (!((live >> i) & 1u)) continue;
+                            if (HAS_RES) {
+                                float4 rr = r4[k & 1][i];
+                                if (res_biased) {
+                                    rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
+                                    rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
+                                }
+                                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                            }
+                            finish(i, x);
+                        }
                     }
                     __syncwarp();
-                    if (HAS_RES && k + 2 < kChunks) load_res(k & 1, k + 2);
+                    if (HAS_RES) {
+                        // buffer k&1 is free: refill it with the chunk two ahead in the CTA's chunk sequence --
+                        // of this tile, or of the CTA's next tile (whose accumulator is still being computed)
+                        if (k + 2 < kChunks) {
+                            load_res(k & 1, cb0 + 32 * (k + 2));
+                        } else {
+                            const int ntile = tile + gridDim.x;
+                            const int nk = kChunks == 1 ? 0 : k + 2 - kChunks;
+                            if (ntile < num_tiles) {
+                                const int nmt = ntile / p.num_n_tiles, nnt = ntile - nmt * p.num_n_tiles;
+                                if (nk == 0) res_rows(nmt);      // rptr / rmask now describe the next tile
+                                load_res(kChunks == 1 ? 0 : (k & 1), nnt * BLOCK_N + col_begin + 32 * nk);
+                                prefetched = true;
+                            } else {
+                                prefetched = false;
+                            }
+                        }
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (tr && warp == 2 && lane == 0 && tile == (int)blockIdx.x) { tr[4] = gtimer(); tr[12] = clock64(); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (tr && threadIdx.x == 0) { tr[5] = gtimer(); tr[13] = clock64(); }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -521,7 +602,7 @@ int pick_block_n(int cout, long long m_tiles, int num_sms) {
 
 template <int BN, int ST, bool RES, bool UP, bool IN16, int EW>
 int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + 2 * kMaxCout * 4 + epi_smem(EW);
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + epi_smem(EW);
     static_assert(smem * (EW == 4 ? 2 : 1) <= 227 * 1024, "smem budget");
     constexpr int kNumThreads = 64 + 32 * EW;
     static bool attr = false;
@@ -584,7 +665,9 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
     const bool k3 = d->kh == 3 && d->kw == 3 && d->pad == 1;
     if (!k1 && !k3) return 0;
     if (d->Cout > kMaxCout || (d->Cout & 3)) return 0;
-    if (d->residual && d->up_src) return 0;
+    if (d->residual && (d->up_src || !k1)) return 0;      // the residual epilogue assumes flat (1x1) rows
+    if (d->up_src && (long long)d->N * d->UH * d->UW * d->Cout >= 0x7fffffffLL) return 0;
+    if ((long long)d->N * d->out_n_stride + d->out_coff >= 0x7fffffffLL) return 0;   // 32-bit element offsets in the epilogue
     if ((reinterpret_cast<uintptr_t>(d->in) & 15) || (reinterpret_cast<uintptr_t>(d->wgt) & 15) ||
         (reinterpret_cast<uintptr_t>(d->out) & 15) || (reinterpret_cast<uintptr_t>(d->out16) & 7))
         return 0;
@@ -596,10 +679,40 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
     return 1;
 }
 
+// ---- optional phase trace (tools/conv_trace.py): 16 words per CTA, kTraceCtas CTAs per launch
+namespace {
+unsigned long long* g_trace = nullptr;
+int g_trace_cap = 0, g_trace_n = 0;
+struct TraceInfo { int v[12]; };
+TraceInfo g_trace_info[4096];
+}  // namespace
+
+extern "C" size_t sb_conv_trace_bytes(int max_launches) {
+    return (size_t)max_launches * kTraceCtas * kTraceWords * sizeof(unsigned long long);
+}
+extern "C" int sb_conv_trace(void* buf, int max_launches) {
+    if (max_launches > 4096) return SB_EINVAL;
+    g_trace = (unsigned long long*)buf;
+    g_trace_cap = buf ? max_launches : 0;
+    g_trace_n = 0;
+    return SB_OK;
+}
+extern "C" int sb_conv_trace_info(int id, int* out12) {
+    if (id < 0 || id >= g_trace_n) return SB_EINVAL;
+    for (int i = 0; i < 12; ++i) out12[i] = g_trace_info[id].v[i];
+    return SB_OK;
+}
+extern "C" int sb_conv_trace_count(void) { return g_trace_n; }
+
 extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     if (!sb_conv2d_tc_supported(d)) return SB_EINVAL;
     TcParams p;
     p.d = *d;
+    // default: release the dependent launch once this CTA's last MMAs are issued -- an early release lets the
+    // next kernel's CTAs sit in griddepcontrol.wait on SMs the other stream's chain could be using
+    static const bool pdl_late = getenv("SB_PDL_LATE") == nullptr || atoi(getenv("SB_PDL_LATE")) != 0;
+    p.pdl_late = pdl_late ? 1 : 0;
+    p.trace = nullptr;
     // spatial 8x16 tiles for 3x3 convs, and for the FPN laterals so that the bilinear upsample taps of a tile
     // (5x9 source pixels) stay in L1 instead of being re-fetched from L2 for every output row
     p.patch = (d->kh == 3 || d->up_src) ? 1 : 0;
@@ -625,10 +738,21 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     // "small" variant (128x128 tiles, half the shared memory, two CTAs per SM): measured slower than the
     // one-CTA-per-SM tiles on every layer shape of this network (tools/conv_bench.py), so it is opt-in only
     bool small = false;
-    if (const char* e = getenv("SB_TC_SMALL")) small = atoi(e) != 0 && d->Cout >= 128 && !d->up_src;
+    if (const char* e = getenv("SB_TC_SMALL")) {
+        const int v = atoi(e);   // 1: every eligible conv, 2: only convs issued with a grid cap (the L/R chains)
+        small = (v == 1 || (v == 2 && d->max_ctas != 0)) && d->Cout >= 128 && !d->up_src;
+    }
     if (small) BN = 128;
     if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256 && !small) BN = v; }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
+    if (g_trace && g_trace_n < g_trace_cap) {
+        const int id = g_trace_n++;
+        p.trace = g_trace + (size_t)id * kTraceCtas * kTraceWords;
+        int* v = g_trace_info[id].v;
+        v[0] = d->Cin; v[1] = d->Cout; v[2] = d->kh; v[3] = (int)p.M; v[4] = BN; v[5] = p.num_m_tiles * p.num_n_tiles;
+        v[6] = p.num_k_blocks; v[7] = d->residual ? 1 : 0; v[8] = d->up_src ? 1 : 0; v[9] = small ? 1 : 0;
+        v[10] = d->max_ctas; v[11] = d->N;
+    }
     CUtensorMap ma, mb;
     if (p.patch) {
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
@@ -652,9 +776,9 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     cudaStream_t st = sb_cs(stream);
     if (small) return launch<128, 2, 4>(ma, mb, p, st);
     switch (BN) {
-        case 32: return launch<32, 6, 8>(ma, mb, p, st);
-        case 64: return launch<64, 6, 8>(ma, mb, p, st);
-        case 256: return launch<256, 3, 8>(ma, mb, p, st);
-        default: return launch<128, 4, 8>(ma, mb, p, st);
+        case 32: return launch<32, 9, 8>(ma, mb, p, st);
+        case 64: return launch<64, 8, 8>(ma, mb, p, st);
+        case 256: return launch<256, 4, 8>(ma, mb, p, st);
+        default: return launch<128, 6, 8>(ma, mb, p, st);
     }
 }

@@ -50,6 +50,8 @@ class StereoRCNNEngine(object):
         self.precision = "fp32-simt" if conv_impl == "simt" else precision
         self.keep32 = False
         self.chain_ctas = int(os.environ.get("SB_CHAIN_CTAS", "0"))
+        self.rpn_streams = os.environ.get("SB_RPN_STREAMS", "1") != "0"
+        self.head_streams = os.environ.get("SB_HEAD_STREAMS", "1") != "0"
         self.side = (torch.cuda.Stream(device=torch.device(device)) if os.environ.get("SB_LR_STREAMS", "1") != "0"
                      and torch.device(device).type == "cuda" else None)
         self.device = torch.device(device)
@@ -275,8 +277,7 @@ class StereoRCNNEngine(object):
         P = sum(h * w for h, w in shapes)
         dev = self.device
         head = torch.empty(B, P, 32, dtype=torch.float32, device=dev)
-        off = 0
-        for f, (h, w) in zip(levels, shapes):
+        def level(f, h, w, off):
             cat = torch.empty(B, h, w, 1024, dtype=f.dtype, device=dev)
             kw = dict(f32=False, out16=cat) if self.half else dict(out=cat, out_mode=ops.ROUND_TF32)
             if B == 1:      # L and R in one launch: image index n = side -> channel offset n * 512
@@ -288,7 +289,20 @@ class StereoRCNNEngine(object):
                                out_coff=side * 512, out_strides=(h * w * 1024, w * 1024, 1024), tag="rpn_conv", **kw)
             self._conv(cat, self.p["rpn_heads"], out=head[:, off:off + h * w],
                        out_strides=(P * 32, w * 32, 32), tag="rpn_heads")
-            off += h * w
+        offs = [0]
+        for h, w in shapes:
+            offs.append(offs[-1] + h * w)
+        fork = self.side is not None and self.rpn_streams
+        if fork:    # the three coarse levels are a handful of tiles each: run them beside the p2 / p3 convs
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                for i in (2, 3, 4):
+                    level(levels[i], shapes[i][0], shapes[i][1], offs[i])
+        for i in ((0, 1) if fork else range(5)):
+            level(levels[i], shapes[i][0], shapes[i][1], offs[i])
+        if fork:
+            main.wait_stream(self.side)
         cls_prob, bbox = ops.rpn_head_epilogue(head, B, P)
         return cls_prob, bbox, shapes
 
@@ -303,13 +317,22 @@ class StereoRCNNEngine(object):
         adt = torch.float16 if h else torch.float32
         rt = not self.exact and not h
         c16 = dict(f32=False, f16=True) if h else {}
-        pooled = torch.empty(R, 7, 7, 512, dtype=adt, device=dev)
-        ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0, round_tf32=rt, half=h)
-        ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256, round_tf32=rt, half=h)
-        x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0",
-                       out_mode=ops.ROUND_TF32, **c16)
-        fc7 = self._conv(x, self.p["RCNN_top.3"], relu=True, tag="top3").view(R, 2048)
-        cls_prob, bbox, dim = ops.box_tail(fc7, *self.fc, n_classes=self.n_classes)
+        def box_head():
+            pooled = torch.empty(R, 7, 7, 512, dtype=adt, device=dev)
+            ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 7, out=pooled, out_coff=0, round_tf32=rt, half=h)
+            ops.roi_align_pyramid_nhwc(fr, im_h, rois_r, 7, out=pooled, out_coff=256, round_tf32=rt, half=h)
+            x = self._conv(pooled.view(R, 1, 1, 7 * 7 * 512), self.p["RCNN_top.0"], relu=True, tag="top0",
+                           out_mode=ops.ROUND_TF32, **c16)
+            fc7 = self._conv(x, self.p["RCNN_top.3"], relu=True, tag="top3").view(R, 2048)
+            return (pooled, fc7) + tuple(ops.box_tail(fc7, *self.fc, n_classes=self.n_classes))
+        fork = self.side is not None and self.head_streams
+        if fork:    # the box head (two FCs with 3 row tiles) is latency-bound: run it beside the keypoint convs
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                pooled, fc7, cls_prob, bbox, dim = box_head()
+        else:
+            pooled, fc7, cls_prob, bbox, dim = box_head()
         pk = ops.roi_align_pyramid_nhwc(fl, im_h, rois_l, 14, round_tf32=rt, half=h)
         x = pk
         for i in range(0, 12, 2):
@@ -321,6 +344,8 @@ class StereoRCNNEngine(object):
                 self._conv(x, self.deconv[a][b], relu=True, out_strides=(28 * 28 * 256, 2 * 28 * 256, 2 * 256),
                            tag="deconv", **kw)
         kp, lb, rb, ka = ops.kpts_tail(up, *self.kpts_class, want_pred_all=True)
+        if fork:
+            main.wait_stream(self.side)
         return dict(pooled_box=pooled, pooled_kpts=pk, fc7=fc7, cls_prob=cls_prob, bbox_pred=bbox,
                     dim_orien_pred=dim, kpts_prob=kp, left_border_prob=lb, right_border_prob=rb,
                     kpts_pred_all=ka)
