@@ -138,6 +138,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+// bring `bytes` (multiple of 16, 16-byte aligned) of global memory into L2 ahead of use; no registers, no smem
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
@@ -153,13 +173,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------ kernel
-struct RowInfo {          // per accumulator row of the current tile (one per lane, in shared memory)
-    long long out_off, res_off, up_off;
-    float ly1, lx1;
-    int flags;            // bit0 valid pixel, bit1 / bit2: the bilinear tap has a +1 row / column
-    int pad;
-};
-
 constexpr size_t epi_smem(int ew) { return (size_t)ew * (32 * 8 * 16); }
 
 struct TcParams {
@@ -176,7 +189,7 @@ struct TcParams {
 
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
     return t;
 }
 constexpr int kTraceWords = 16, kTraceCtas = 304;
@@ -322,9 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr int kChunks = kColsPerWarp / 32;
         const int col_begin = half * kColsPerWarp;
         const bool has_cols = col_begin < BLOCK_N;
-        float4* stg = epi_stage + ew * (32 * 8);
-        RowInfo* ri = reinterpret_cast<RowInfo*>(stg);      // 32 * sizeof(RowInfo) <= the 4 KB staging tile
-        static_assert(32 * sizeof(RowInfo) <= 32 * 8 * sizeof(float4), "row exchange fits the staging tile");
+        const uint32_t stg = smem_u32(epi_stage + ew * (32 * 8));      // this warp's 4 KB staging tile (shared-space address)
         int acc = 0;
         uint32_t acc_phase = 0;
         float rh = 0.f, rw = 0.f;
@@ -355,8 +366,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 r4[buf][i] = (i < live) ? __ldg(reinterpret_cast<const float4*>(rbase + i * rstep + cbase))
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        // Residual rows of a tile two ahead are pulled into L2 with a bulk prefetch (one row segment per lane): in
+        // layers 1-2 the residual stream lives in HBM, and the register prefetch alone keeps too few bytes in
+        // flight (64 KB per SM against a ~2 us DRAM round trip) to fill the memory pipe.
+        auto prefetch_res_tile = [&](int t) {
+            if (t >= num_tiles) return;
+            const int pmt = t / p.num_n_tiles, pnt = t - pmt * p.num_n_tiles;
+            const long long m = (long long)pmt * BLOCK_M + q * 32 + lane;
+            const int c0 = pnt * BLOCK_N + col_begin;
+            if (m < p.M && c0 < d.Cout) {
+                const int ncols = min(kColsPerWarp, d.Cout - c0);
+                prefetch_l2_bulk(d.residual + m * d.res_ld + c0, (uint32_t)ncols * 4u);
+            }
+        };
+        if (HAS_RES && has_cols) prefetch_res_tile(blockIdx.x + gridDim.x);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+            if (HAS_RES && has_cols) prefetch_res_tile(tile + 2 * gridDim.x);
             unsigned ooff[8];          // element offsets < 2^31 (checked on the host)
             unsigned vmask = 0;
             int uoff[8];
@@ -383,36 +409,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     ho = (int)(rem / (unsigned)d.Wo);
                     wo = (int)(rem - (unsigned)ho * (unsigned)d.Wo);
                 }
-                RowInfo inf;
-                inf.out_off = (long long)n_img * d.out_n_stride + (long long)ho * d.out_h_stride +
-                              (long long)wo * d.out_w_stride + d.out_coff;
-                inf.res_off = 0;
-                inf.flags = valid ? 1 : 0;
-                inf.up_off = 0; inf.ly1 = 0.f; inf.lx1 = 0.f;
+                // one 16-byte record per row {output offset, upsample source offset, ly1, lx1} goes through the
+                // (idle) staging tile; the three per-row flags travel as ballots
+                const long long out_off = (long long)n_img * d.out_n_stride + (long long)ho * d.out_h_stride +
+                                          (long long)wo * d.out_w_stride + d.out_coff;
+                uint4 rec = make_uint4((unsigned)out_off, 0u, 0u, 0u);
+                bool by = false, bx = false;
                 if (HAS_UP && valid) {
                     const float sy = __fmul_rn(rh, (float)ho), sx = __fmul_rn(rw, (float)wo);
                     const int y1 = (int)sy, x1 = (int)sx;
-                    if (y1 < d.UH - 1) inf.flags |= 2;
-                    if (x1 < d.UW - 1) inf.flags |= 4;
-                    inf.ly1 = sy - (float)y1;
-                    inf.lx1 = sx - (float)x1;
-                    inf.up_off = (((long long)n_img * d.UH + y1) * d.UW + x1) * d.Cout;
+                    by = y1 < d.UH - 1;
+                    bx = x1 < d.UW - 1;
+                    rec.y = (unsigned)((((long long)n_img * d.UH + y1) * d.UW + x1) * d.Cout);
+                    rec.z = __float_as_uint(sy - (float)y1);
+                    rec.w = __float_as_uint(sx - (float)x1);
                 }
-                __syncwarp();           // the previous tile's staging reads are done
-                ri[lane] = inf;
+                const unsigned bal_v = __ballot_sync(0xffffffffu, valid);
+                const unsigned bal_y = HAS_UP ? __ballot_sync(0xffffffffu, by) : 0u;
+                const unsigned bal_x = HAS_UP ? __ballot_sync(0xffffffffu, bx) : 0u;
+                sts128u(stg + lane * 16, rec);          // (the previous tile's staging reads ended with a __syncwarp)
                 __syncwarp();
                 // rows this lane touches in the coalesced domain: 4*i + rsub, i = 0..7
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const RowInfo& o = ri[4 * i + rsub];
-                    ooff[i] = (unsigned)o.out_off + 4u * c4;
-                    vmask |= (unsigned)(o.flags & 1) << i;
+                    const int r = 4 * i + rsub;
+                    const uint4 o = lds128u(stg + r * 16);
+                    ooff[i] = o.x + 4u * c4;
+                    vmask |= ((bal_v >> r) & 1u) << i;
                     if (HAS_UP) {
-                        uoff[i] = (int)o.up_off;
-                        uly[i] = o.ly1;
-                        ulx[i] = o.lx1;
-                        fy |= (unsigned)((o.flags >> 1) & 1) << i;
-                        fx |= (unsigned)((o.flags >> 2) & 1) << i;
+                        uoff[i] = (int)o.y;
+                        uly[i] = __uint_as_float(o.z);
+                        ulx[i] = __uint_as_float(o.w);
+                        fy |= ((bal_y >> r) & 1u) << i;
+                        fx |= ((bal_x >> r) & 1u) << i;
                     }
                 }
                 __syncwarp();           // staging tile free again
@@ -428,12 +457,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (has_cols) {
+                // Each chunk runs in straight-line phases over the lane's 8 row quads (loads, math, stores): with
+                // two epilogue warps per scheduler there is nothing else to hide latency behind, so the
+                // instruction-level parallelism has to come from inside the warp (no per-row branches).
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_begin);
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
 #pragma unroll
                 for (int k = 0; k < kChunks; ++k) {
-                    const int cc = col_begin + 32 * k;
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + cc), v);
-                    const int cbase = nt * BLOCK_N + cc;
+                    const int cbase = nt * BLOCK_N + col_begin + 32 * k;
                     const int cidx = cbase + 4 * c4;
                     const bool col_ok = cidx < d.Cout;
                     const unsigned live = col_ok ? vmask : 0u;
@@ -445,37 +477,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
-                                                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        sts128(stg + (lane * 8 + (j ^ (lane & 7))) * 16,
+                               make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     __syncwarp();
-                    auto finish = [&](int i, float4 x) {       // relu / store mode / fp32 + fp16 stores of one row quad
-                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                        if (out_mode == 1) {
-                            x.x = sb_round_tf32(x.x); x.y = sb_round_tf32(x.y); x.z = sb_round_tf32(x.z); x.w = sb_round_tf32(x.w);
-                        } else if (out_mode == 2) {
-                            x.x = sb_bias_tf32(x.x); x.y = sb_bias_tf32(x.y); x.z = sb_bias_tf32(x.z); x.w = sb_bias_tf32(x.w);
-                        }
-                        if (d.out) *reinterpret_cast<float4*>(d.out + ooff[i] + cbase) = x;
-                        if (d.out16) {   // fp16 twin (round to nearest) for the next tensor-core consumer
-                            __half2 lo = __floats2half2_rn(out_mode == 2 ? sb_unbias_tf32(x.x) : x.x, out_mode == 2 ? sb_unbias_tf32(x.y) : x.y);
-                            __half2 hi = __floats2half2_rn(out_mode == 2 ? sb_unbias_tf32(x.z) : x.z, out_mode == 2 ? sb_unbias_tf32(x.w) : x.w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + cbase) = pk;
-                        }
-                    };
-                    auto staged = [&](int i) {                 // accumulator quad of row 4*i+rsub, scale / shift applied
+                    // the next chunk's accumulator columns travel TMEM -> registers while this chunk is finished
+                    constexpr bool kEarlyLd = !HAS_RES && !HAS_UP;       // the other variants have no registers to spare
+                    if (kEarlyLd && k + 1 < kChunks) tmem_ld32(taddr + 32 * (k + 1), v);
+                    float4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + rsub;
-                        float4 x = stg[r * 8 + (c4 ^ (r & 7))];
-                        x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
-                        x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-                        return x;
-                    };
+                        x[i] = lds128(stg + (r * 8 + (c4 ^ (r & 7))) * 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        x[i].x = fmaf(x[i].x, sc.x, sh.x); x[i].y = fmaf(x[i].y, sc.y, sh.y);
+                        x[i].z = fmaf(x[i].z, sc.z, sh.z); x[i].w = fmaf(x[i].w, sc.w, sh.w);
+                    }
+                    if (HAS_RES) {
+                        if (res_biased) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4& rr = r4[k & 1][i];
+                                rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
+                                rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 rr = r4[k & 1][i];
+                            x[i].x += rr.x; x[i].y += rr.y; x[i].z += rr.z; x[i].w += rr.w;
+                        }
+                    }
                     if (HAS_UP) {
                         const float* ubase = d.up_src + (col_ok ? cidx : 0);
                         const long long ustep_y = (long long)d.UW * d.Cout;
-#pragma unroll
                         constexpr int UB = 2;                     // rows per batch: 4 * UB independent tap loads in flight
 #pragma unroll
                         for (int hh = 0; hh < 8 / UB; ++hh) {
@@ -494,31 +531,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int ii = 0; ii < UB; ++ii) {
                                 const int i = hh * UB + ii;
-                                float4 x = staged(i);
-                                if (!((live >> i) & 1u)) continue;
                                 const float4 a = ta[ii], bq = tb[ii], g = tg[ii], h = th[ii];
                                 const float ly1 = uly[i], ly0 = 1.f - ly1, lx1 = ulx[i], lx0 = 1.f - lx1;
-                                x.x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
-                                x.y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
-                                x.z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
-                                x.w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
-                                finish(i, x);
+                                x[i].x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
+                                x[i].y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
+                                x[i].z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
+                                x[i].w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
                             }
                         }
-                    } else {
+                    }
+                    if (relu) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float4 x = staged(i);
-                            if (!((live >> i) & 1u)) continue;
-                            if (HAS_RES) {
-                                float4 rr = r4[k & 1][i];
-                                if (res_biased) {
-                                    rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
-                                    rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
-                                }
-                                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                            x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f);
+                            x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
+                        }
+                    }
+                    if (out_mode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            x[i].x = sb_round_tf32(x[i].x); x[i].y = sb_round_tf32(x[i].y);
+                            x[i].z = sb_round_tf32(x[i].z); x[i].w = sb_round_tf32(x[i].w);
+                        }
+                    } else if (out_mode == 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            x[i].x = sb_bias_tf32(x[i].x); x[i].y = sb_bias_tf32(x[i].y);
+                            x[i].z = sb_bias_tf32(x[i].z); x[i].w = sb_bias_tf32(x[i].w);
+                        }
+                    }
+                    if (d.out) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if ((live >> i) & 1u) *reinterpret_cast<float4*>(d.out + ooff[i] + cbase) = x[i];
+                    }
+                    if (d.out16) {   // fp16 twin (round to nearest) for the next tensor-core consumer
+                        if (out_mode == 2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                x[i].x = sb_unbias_tf32(x[i].x); x[i].y = sb_unbias_tf32(x[i].y);
+                                x[i].z = sb_unbias_tf32(x[i].z); x[i].w = sb_unbias_tf32(x[i].w);
                             }
-                            finish(i, x);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __half2 lo = __floats2half2_rn(x[i].x, x[i].y);
+                            __half2 hi = __floats2half2_rn(x[i].z, x[i].w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            if ((live >> i) & 1u)
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + cbase) = pk;
                         }
                     }
                     __syncwarp();
@@ -532,7 +595,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             const int nk = kChunks == 1 ? 0 : k + 2 - kChunks;
                             if (ntile < num_tiles) {
                                 const int nmt = ntile / p.num_n_tiles, nnt = ntile - nmt * p.num_n_tiles;
-                                if (nk == 0) res_rows(nmt);      // rptr / rmask now describe the next tile
+                                if (nk == 0) res_rows(nmt);      // rbase / rrows now describe the next tile
                                 load_res(kChunks == 1 ? 0 : (k & 1), nnt * BLOCK_N + col_begin + 32 * nk);
                                 prefetched = true;
                             } else {
@@ -540,6 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     }
+                    if (!kEarlyLd && k + 1 < kChunks) tmem_ld32(taddr + 32 * (k + 1), v);
                 }
             }
             tc_fence_before();
