@@ -330,8 +330,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // four rows at a time before they are consumed.
         const int q = warp & 3;
         const int ew = warp - 2;
-        const int half = EW == 8 ? (ew >> 2) : 0;
-        constexpr int kColsPerWarp = EW == 8 ? (BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32) : BLOCK_N;
+        // EW / 4 warps share each TMEM lane quarter and split the tile's columns between them.  EW = 16 is the
+        // variant for epilogue-bound convs (few K-steps per tile): four warps per scheduler hide each other's
+        // latencies, at 112 registers per thread -- so it reads the residual where it is used (L2 hits, thanks to
+        // the bulk prefetch) instead of through the 64-register prefetch ring.
+        constexpr int kParts = EW / 4;
+        const int half = ew >> 2;          // which column part this warp owns (0 for EW = 4)
+        constexpr int kColsPerWarp = BLOCK_N / kParts >= 32 ? BLOCK_N / kParts : 32;
+        constexpr bool kResRing = HAS_RES && EW <= 8;
         constexpr int kChunks = kColsPerWarp / 32;
         const int col_begin = half * kColsPerWarp;
         const bool has_cols = col_begin < BLOCK_N;
@@ -358,6 +364,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const long long left = p.M - m0;                     // rows m0, m0+4, ... < M
             rrows = left <= 0 ? 0 : (left >= 32 ? 8 : (int)((left + 3) >> 2));
             rbase = d.residual + (left <= 0 ? 0 : m0) * d.res_ld + 4 * c4;
+        };
+        // folded-BN scale / shift (or bias) of the lane's four channels, fetched one chunk ahead
+        float4 sc_n = make_float4(1.f, 1.f, 1.f, 1.f), sh_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_scale_shift = [&](int cidx) {
+            const bool ok = cidx < d.Cout;
+            sc_n = (d.scale && ok) ? __ldg(reinterpret_cast<const float4*>(d.scale + cidx)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            sh_n = (d.shift && ok) ? __ldg(reinterpret_cast<const float4*>(d.shift + cidx)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         auto load_res = [&](int buf, int cbase) {
             const int live = (cbase + 4 * c4 < d.Cout) ? rrows : 0;
@@ -434,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int i = 0; i < 8; ++i) {
                     const int r = 4 * i + rsub;
                     const uint4 o = lds128u(stg + r * 16);
-                    ooff[i] = o.x + 4u * c4;
+                    ooff[i] = o.x + 4u * c4 + (unsigned)(nt * BLOCK_N + col_begin);     // + the warp's first column
                     vmask |= ((bal_v >> r) & 1u) << i;
                     if (HAS_UP) {
                         uoff[i] = (int)o.y;
@@ -447,13 +460,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 __syncwarp();           // staging tile free again
             }
             const int cb0 = nt * BLOCK_N + col_begin;
-            if (HAS_RES && has_cols && !prefetched) {
+            if (HAS_RES && !kResRing && has_cols) res_rows(mt);
+            if (kResRing && has_cols && !prefetched) {
                 // the first tile's residual rows are requested before its accumulator is complete, so their
                 // latency hides behind the MMA main loop
                 res_rows(mt);
                 load_res(0, cb0);
                 if (kChunks > 1) load_res(1, cb0 + 32);
             }
+            if (has_cols) load_scale_shift(cb0 + 4 * c4);      // chunk 0's: in flight while the accumulator completes
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             if (has_cols) {
@@ -463,17 +478,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_begin);
                 uint32_t v[32];
                 tmem_ld32(taddr, v);
-#pragma unroll
+                constexpr int kUnroll = HAS_UP ? 1 : kChunks;      // (the upsample-add chunk body is register-bound: keep chunks apart)
+#pragma unroll kUnroll
                 for (int k = 0; k < kChunks; ++k) {
                     const int cbase = nt * BLOCK_N + col_begin + 32 * k;
                     const int cidx = cbase + 4 * c4;
                     const bool col_ok = cidx < d.Cout;
                     const unsigned live = col_ok ? vmask : 0u;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (col_ok) {
-                        if (d.scale) { sc.x = __ldg(d.scale + cidx); sc.y = __ldg(d.scale + cidx + 1); sc.z = __ldg(d.scale + cidx + 2); sc.w = __ldg(d.scale + cidx + 3); }
-                        if (d.shift) { sh.x = __ldg(d.shift + cidx); sh.y = __ldg(d.shift + cidx + 1); sh.z = __ldg(d.shift + cidx + 2); sh.w = __ldg(d.shift + cidx + 3); }
-                    }
+                    const float4 sc = sc_n, sh = sh_n;
+                    if (k + 1 < kChunks) load_scale_shift(cb0 + 32 * (k + 1) + 4 * c4);      // for the next chunk
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -482,110 +495,130 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     __syncwarp();
                     // the next chunk's accumulator columns travel TMEM -> registers while this chunk is finished
-                    constexpr bool kEarlyLd = !HAS_RES && !HAS_UP;       // the other variants have no registers to spare
+                    constexpr bool kEarlyLd = !HAS_RES && !HAS_UP && EW <= 8;   // the other variants have no registers to spare
                     if (kEarlyLd && k + 1 < kChunks) tmem_ld32(taddr + 32 * (k + 1), v);
-                    float4 x[8];
+                    // rows per pass: the upsample-add variant keeps 16 tap registers per row pair, so it walks the
+                    // lane's 8 row quads in two passes of 4 to stay inside the register file
+                    constexpr int XR = HAS_UP ? 4 : 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 4 * i + rsub;
-                        x[i] = lds128(stg + (r * 8 + (c4 ^ (r & 7))) * 16);
-                    }
+                    for (int pass = 0; pass < 8 / XR; ++pass) {
+                        float4 x[XR];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        x[i].x = fmaf(x[i].x, sc.x, sh.x); x[i].y = fmaf(x[i].y, sc.y, sh.y);
-                        x[i].z = fmaf(x[i].z, sc.z, sh.z); x[i].w = fmaf(x[i].w, sc.w, sh.w);
-                    }
-                    if (HAS_RES) {
-                        if (res_biased) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float4& rr = r4[k & 1][i];
-                                rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
-                                rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
-                            }
+                        for (int ii = 0; ii < XR; ++ii) {
+                            const int r = 4 * (pass * XR + ii) + rsub;
+                            x[ii] = lds128(stg + (r * 8 + (c4 ^ (r & 7))) * 16);
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 rr = r4[k & 1][i];
-                            x[i].x += rr.x; x[i].y += rr.y; x[i].z += rr.z; x[i].w += rr.w;
+                        for (int ii = 0; ii < XR; ++ii) {
+                            x[ii].x = fmaf(x[ii].x, sc.x, sh.x); x[ii].y = fmaf(x[ii].y, sc.y, sh.y);
+                            x[ii].z = fmaf(x[ii].z, sc.z, sh.z); x[ii].w = fmaf(x[ii].w, sc.w, sh.w);
                         }
-                    }
-                    if (HAS_UP) {
-                        const float* ubase = d.up_src + (col_ok ? cidx : 0);
-                        const long long ustep_y = (long long)d.UW * d.Cout;
-                        constexpr int UB = 2;                     // rows per batch: 4 * UB independent tap loads in flight
+                        if (HAS_RES) {
+                            if (kResRing && res_biased) {
 #pragma unroll
-                        for (int hh = 0; hh < 8 / UB; ++hh) {
-                            float4 ta[UB], tb[UB], tg[UB], th[UB];
-#pragma unroll
-                            for (int ii = 0; ii < UB; ++ii) {
-                                const int i = hh * UB + ii;
-                                const float* u00 = ubase + uoff[i];
-                                const long long dx = ((fx >> i) & 1u) ? d.Cout : 0;
-                                const long long dy = ((fy >> i) & 1u) ? ustep_y : 0;
-                                ta[ii] = __ldg(reinterpret_cast<const float4*>(u00));
-                                tb[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dx));
-                                tg[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dy));
-                                th[ii] = __ldg(reinterpret_cast<const float4*>(u00 + dy + dx));
+                                for (int ii = 0; ii < XR; ++ii) {
+                                    float4& rr = r4[k & 1][pass * XR + ii];
+                                    rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
+                                    rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
+                                }
                             }
 #pragma unroll
-                            for (int ii = 0; ii < UB; ++ii) {
-                                const int i = hh * UB + ii;
-                                const float4 a = ta[ii], bq = tb[ii], g = tg[ii], h = th[ii];
-                                const float ly1 = uly[i], ly0 = 1.f - ly1, lx1 = ulx[i], lx0 = 1.f - lx1;
-                                x[i].x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
-                                x[i].y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
-                                x[i].z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
-                                x[i].w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
+                            for (int ii = 0; ii < XR; ++ii) {
+                                float4 rr;
+                                if (kResRing) {
+                                    rr = r4[k & 1][pass * XR + ii];
+                                } else {
+                                    const int i = pass * XR + ii;
+                                    rr = (col_ok && i < rrows) ? __ldg(reinterpret_cast<const float4*>(rbase + i * rstep + cbase))
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (res_biased) {
+                                        rr.x = sb_unbias_tf32(rr.x); rr.y = sb_unbias_tf32(rr.y);
+                                        rr.z = sb_unbias_tf32(rr.z); rr.w = sb_unbias_tf32(rr.w);
+                                    }
+                                }
+                                x[ii].x += rr.x; x[ii].y += rr.y; x[ii].z += rr.z; x[ii].w += rr.w;
                             }
                         }
-                    }
-                    if (relu) {
+                        if (HAS_UP) {
+                            const float* ubase = d.up_src + (col_ok ? cidx : 0);
+                            const long long ustep_y = (long long)d.UW * d.Cout;
+                            constexpr int UB = 2;                     // rows per batch: 4 * UB independent tap loads in flight
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f);
-                            x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
-                        }
-                    }
-                    if (out_mode == 1) {
+                            for (int hh = 0; hh < XR / UB; ++hh) {
+                                float4 ta[UB], tb[UB], tg[UB], th[UB];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            x[i].x = sb_round_tf32(x[i].x); x[i].y = sb_round_tf32(x[i].y);
-                            x[i].z = sb_round_tf32(x[i].z); x[i].w = sb_round_tf32(x[i].w);
-                        }
-                    } else if (out_mode == 2) {
+                                for (int jj = 0; jj < UB; ++jj) {
+                                    const int i = pass * XR + hh * UB + jj;
+                                    const float* u00 = ubase + uoff[i];
+                                    const long long dx = ((fx >> i) & 1u) ? d.Cout : 0;
+                                    const long long dy = ((fy >> i) & 1u) ? ustep_y : 0;
+                                    ta[jj] = __ldg(reinterpret_cast<const float4*>(u00));
+                                    tb[jj] = __ldg(reinterpret_cast<const float4*>(u00 + dx));
+                                    tg[jj] = __ldg(reinterpret_cast<const float4*>(u00 + dy));
+                                    th[jj] = __ldg(reinterpret_cast<const float4*>(u00 + dy + dx));
+                                }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            x[i].x = sb_bias_tf32(x[i].x); x[i].y = sb_bias_tf32(x[i].y);
-                            x[i].z = sb_bias_tf32(x[i].z); x[i].w = sb_bias_tf32(x[i].w);
-                        }
-                    }
-                    if (d.out) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if ((live >> i) & 1u) *reinterpret_cast<float4*>(d.out + ooff[i] + cbase) = x[i];
-                    }
-                    if (d.out16) {   // fp16 twin (round to nearest) for the next tensor-core consumer
-                        if (out_mode == 2) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                x[i].x = sb_unbias_tf32(x[i].x); x[i].y = sb_unbias_tf32(x[i].y);
-                                x[i].z = sb_unbias_tf32(x[i].z); x[i].w = sb_unbias_tf32(x[i].w);
+                                for (int jj = 0; jj < UB; ++jj) {
+                                    const int ii = hh * UB + jj, i = pass * XR + ii;
+                                    const float4 a = ta[jj], bq = tb[jj], g = tg[jj], h = th[jj];
+                                    const float ly1 = uly[i], ly0 = 1.f - ly1, lx1 = ulx[i], lx0 = 1.f - lx1;
+                                    x[ii].x += ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * g.x + lx1 * h.x);
+                                    x[ii].y += ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * g.y + lx1 * h.y);
+                                    x[ii].z += ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * g.z + lx1 * h.z);
+                                    x[ii].w += ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * g.w + lx1 * h.w);
+                                }
                             }
                         }
+                        if (relu) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __half2 lo = __floats2half2_rn(x[i].x, x[i].y);
-                            __half2 hi = __floats2half2_rn(x[i].z, x[i].w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                            if ((live >> i) & 1u)
-                                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + cbase) = pk;
+                            for (int ii = 0; ii < XR; ++ii) {
+                                x[ii].x = fmaxf(x[ii].x, 0.f); x[ii].y = fmaxf(x[ii].y, 0.f);
+                                x[ii].z = fmaxf(x[ii].z, 0.f); x[ii].w = fmaxf(x[ii].w, 0.f);
+                            }
+                        }
+                        if (out_mode == 1) {
+#pragma unroll
+                            for (int ii = 0; ii < XR; ++ii) {
+                                x[ii].x = sb_round_tf32(x[ii].x); x[ii].y = sb_round_tf32(x[ii].y);
+                                x[ii].z = sb_round_tf32(x[ii].z); x[ii].w = sb_round_tf32(x[ii].w);
+                            }
+                        } else if (out_mode == 2) {
+#pragma unroll
+                            for (int ii = 0; ii < XR; ++ii) {
+                                x[ii].x = sb_bias_tf32(x[ii].x); x[ii].y = sb_bias_tf32(x[ii].y);
+                                x[ii].z = sb_bias_tf32(x[ii].z); x[ii].w = sb_bias_tf32(x[ii].w);
+                            }
+                        }
+                        if (d.out) {
+#pragma unroll
+                            for (int ii = 0; ii < XR; ++ii) {
+                                const int i = pass * XR + ii;
+                                if ((live >> i) & 1u) *reinterpret_cast<float4*>(d.out + ooff[i] + 32 * k) = x[ii];
+                            }
+                        }
+                        if (d.out16) {   // fp16 twin (round to nearest) for the next tensor-core consumer
+                            if (out_mode == 2) {
+#pragma unroll
+                                for (int ii = 0; ii < XR; ++ii) {
+                                    x[ii].x = sb_unbias_tf32(x[ii].x); x[ii].y = sb_unbias_tf32(x[ii].y);
+                                    x[ii].z = sb_unbias_tf32(x[ii].z); x[ii].w = sb_unbias_tf32(x[ii].w);
+                                }
+                            }
+#pragma unroll
+                            for (int ii = 0; ii < XR; ++ii) {
+                                const int i = pass * XR + ii;
+                                __half2 lo = __floats2half2_rn(x[ii].x, x[ii].y);
+                                __half2 hi = __floats2half2_rn(x[ii].z, x[ii].w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                                if ((live >> i) & 1u)
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(d.out16) + ooff[i] + 32 * k) = pk;
+                            }
                         }
                     }
                     __syncwarp();
-                    if (HAS_RES) {
+                    if (kResRing) {
                         // buffer k&1 is free: refill it with the chunk two ahead in the CTA's chunk sequence --
                         // of this tile, or of the CTA's next tile (whose accumulator is still being computed)
                         if (k + 2 < kChunks) {
@@ -706,6 +739,15 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
     return SB_OK;
 }
 
+// 16 epilogue warps (576 threads): plain and residual epilogues only
+template <int BN, int ST>
+int launch16(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    const bool res = p.d.residual != nullptr;
+    if (p.d.in_dtype == 1)
+        return res ? launch_t<BN, ST, true, false, true, 16>(ma, mb, p, st) : launch_t<BN, ST, false, false, true, 16>(ma, mb, p, st);
+    return res ? launch_t<BN, ST, true, false, false, 16>(ma, mb, p, st) : launch_t<BN, ST, false, false, false, 16>(ma, mb, p, st);
+}
+
 template <int BN, int ST, int EW>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
     const bool res = p.d.residual != nullptr, up = p.d.up_src != nullptr;   // never both (supported())
@@ -737,6 +779,7 @@ extern "C" int sb_conv2d_tc_supported(const sb_conv_desc* d) {
         return 0;
     if ((d->out_coff & 3) || (d->out_n_stride & 3) || (d->out_h_stride & 3) || (d->out_w_stride & 3)) return 0;
     if (d->residual && ((d->res_ld & 3) || (reinterpret_cast<uintptr_t>(d->residual) & 15))) return 0;
+    if ((reinterpret_cast<uintptr_t>(d->scale) & 15) || (reinterpret_cast<uintptr_t>(d->shift) & 15)) return 0;   // float4 loads
     if (d->up_src && ((d->Cout & 3) || (reinterpret_cast<uintptr_t>(d->up_src) & 15))) return 0;
     if (d->Ho != d->H || d->Wo != d->W) return 0;
     if ((long long)d->N * d->Ho * d->Wo >= 0x7fffffffLL) return 0;
@@ -839,6 +882,13 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     }
     cudaStream_t st = sb_cs(stream);
     if (small) return launch<128, 2, 4>(ma, mb, p, st);
+    // epilogue-bound shapes (at most 8 K-steps per tile: the 1x1 convs of the bottlenecks, the deconv quarters)
+    // can run with 16 epilogue warps: SB_TC_EW16 = 0 never (default), 1 by this rule, 2 whenever the tile is wide
+    // enough.  Measured (tools/epi_bench.py, bench.py): no faster than 8 warps -- the epilogue is bound by the SM's
+    // store / load path, not by per-warp latency -- so it stays opt-in.
+    static const int ew16 = getenv("SB_TC_EW16") ? atoi(getenv("SB_TC_EW16")) : 0;
+    if (BN >= 128 && !d->up_src && (ew16 == 2 || (ew16 == 1 && p.num_k_blocks <= 8)))
+        return BN == 256 ? launch16<256, 3>(ma, mb, p, st) : launch16<128, 5>(ma, mb, p, st);
     switch (BN) {
         case 32: return launch<32, 9, 8>(ma, mb, p, st);
         case 64: return launch<64, 8, 8>(ma, mb, p, st);

@@ -6,10 +6,10 @@ mkdir -p gpurun_out
 run() {
   local tag="$1"; shift
   local line
-  line=$(env "$@" timeout 180 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1)
+  line=$(env "$@" timeout 180 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1)
   echo "$tag | $(echo "$line" | python -c 'import sys,json
 try:
-    d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["value"], d.get("e2e",{}).get("value"))
+    d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["value"], d.get("e2e",{}).get("value"), (d.get("single_stream") or {}).get("ms_per_step"))
 except Exception as e: print("ERR", e)')" | tee -a $out
 }
 while read -r tag vars; do

@@ -24,9 +24,13 @@ def timeit(d, reps=40):
 
 def main():
     dev = "cuda"
+    only_shape = sys.argv[1] if len(sys.argv) > 1 else None       # e.g. "L1 conv3"
+    only_tag = sys.argv[2] if len(sys.argv) > 2 else None         # e.g. "o32+o16+res" (for ncu captures)
     for name, N, H, W, Ci, Co, k in (("L3 conv3", 1, 38, 125, 256, 1024, 1), ("L3 conv3 x2", 2, 38, 125, 256, 1024, 1),
                                      ("L3 conv1", 1, 38, 125, 1024, 256, 1), ("L3 conv2", 1, 38, 125, 256, 256, 3),
                                      ("L2 conv3", 2, 75, 249, 128, 512, 1), ("L1 conv3", 2, 150, 497, 64, 256, 1)):
+        if only_shape and only_shape != name:
+            continue
         x = torch.randn(N, H, W, Ci, device=dev).half()
         w = (torch.randn(Co, k, k, Ci, device=dev) * 0.05).half()
         sc, sh = torch.rand(Co, device=dev) + 0.5, torch.randn(Co, device=dev)
@@ -38,7 +42,7 @@ def main():
             line = "%-12s cap %3d |" % (name, cap)
             for tag, out, out16, res in (("o32+o16+res", o32, o16, r), ("o32+res", o32, None, r), ("o16+res", None, o16, r),
                                          ("o32+o16", o32, o16, None), ("o32", o32, None, None), ("o16", None, o16, None)):
-                if res is not None and k != 1:
+                if (res is not None and k != 1) or (only_tag and (only_tag != tag or cap)):
                     continue
                 d = ops.conv_desc(x, w, out, Ci, Co, k, k, 1, k // 2, H, W, scale=sc, shift=sh, residual=res, relu=True,
                                   out16=out16, max_ctas=cap)
