@@ -37,7 +37,7 @@ REC_COLS = 2 + 8 + 8 + 10 + 5        # scores, boxes L/R, dim_orien, kpts  (per 
 # algorithmic MACs per *pair* at test (SURVEY 8 header / BASELINE.md 3), for the roofline line
 TC_GMACS_PER_PAIR = 2 * (15.88 + 22.64 + 123.58 + 17.89 + 66.99 + 117.37) + 2.45 + 16.7 + 223.9
 # (the 2 x 2.81 GMAC stem GEMM is executed on the tensor cores too but not counted as algorithmic work here)
-CONV_DRAM_BYTES_PER_STEP = 5.852e9     # profiles/r01_conv_dram.md (fp16-operand default)
+CONV_DRAM_BYTES_PER_STEP = 5.654e9     # profiles/r01b_conv_dram.md (fp16-operand default, 213 conv launches)
 
 
 def peaks():
@@ -310,8 +310,8 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::%s implicit GEMM, all conv/FC launches of one step)" % ("f16" if half else "tf32"),
                 "achieved": round(tflops, 2), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": round(tflops / pk["bf16_tflops_sustained"], 4),
-                # dram__bytes_read+write summed over the 133 conv launches of one step, ncu capture of this same
-                # command (profiles/r01_conv_dram.md); algorithmic FLOPs per step = 2 * 0.978 TMAC
+                # dram__bytes_read+write summed over the 213 conv launches of one step, ncu capture of this same
+                # command (profiles/r01b_conv_dram.md); algorithmic FLOPs per step = 2 * 0.978 TMAC
                 "traffic": CONV_DRAM_BYTES_PER_STEP if half else None,
                 "traffic_unit": "bytes per step (all conv launches)",
                 "peak_source": pk["src"] + " cuBLAS bf16 sustained" + ("" if half else " (kind::tf32 issues at half that rate)"),
