@@ -39,7 +39,7 @@ class PackedConv(object):
 class StereoRCNNEngine(object):
     """state_dict uses the reference's key names (RCNN_layer1.0.0.conv1.weight, ...)"""
 
-    def __init__(self, state_dict, device="cuda", n_classes=2, conv_impl="auto", precision=None):
+    def __init__(self, state_dict, device="cuda", n_classes=2, conv_impl="auto", precision=None, lr_streams=None):
         """precision: "tf32" (fp32 storage, kind::tf32) or "fp16" (fp16 conv operands, kind::f16, fp32 accumulate
         and fp32 residual stream); default from $SB_PRECISION, else "fp16" (same measured accuracy as tf32 --
         both round operands to an 11-bit significand -- at twice the MMA rate and half the activation bytes).  conv_impl="simt" forces exact fp32."""
@@ -52,8 +52,13 @@ class StereoRCNNEngine(object):
         self.chain_ctas = int(os.environ.get("SB_CHAIN_CTAS", "0"))
         self.rpn_streams = os.environ.get("SB_RPN_STREAMS", "1") != "0"
         self.head_streams = os.environ.get("SB_HEAD_STREAMS", "1") != "0"
-        self.side = (torch.cuda.Stream(device=torch.device(device)) if os.environ.get("SB_LR_STREAMS", "1") != "0"
-                     and torch.device(device).type == "cuda" else None)
+        # lr_streams: run layers 3-4 of the left and the right image as two concurrent chains (lowest latency of a
+        # single pair).  With several independent pairs in flight the SMs are already full and the batched chain
+        # (fewer, wider tiles) costs less SM time: callers that pipeline pairs pass lr_streams=False.
+        if lr_streams is None:
+            lr_streams = os.environ.get("SB_LR_STREAMS", "1") != "0"
+        self.lr_streams = bool(lr_streams)
+        self.side = torch.cuda.Stream(device=torch.device(device)) if torch.device(device).type == "cuda" else None
         self.device = torch.device(device)
         self.n_classes = n_classes
         self.conv_impl = conv_impl
@@ -246,7 +251,7 @@ class StereoRCNNEngine(object):
                     y32, y16 = self._bottleneck16(y32, y16, "RCNN_layer%d.0.%d" % (li + 1, bi),
                                                   STRIDES[li] if bi == 0 else 1, bi == 0,
                                                   out=(dst[0][sl], dst[1][sl]) if last else None)
-        if self.side is not None:
+        if self.side is not None and self.lr_streams:
             main = torch.cuda.current_stream()
             self.side.wait_stream(main)
             self.max_ctas = self.chain_ctas      # each chain keeps to half of the SMs so that both really co-run
