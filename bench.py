@@ -311,7 +311,7 @@ def run_ours(args):
     cpu_base = None
     if rank == 0:
         pk = peaks()
-        conv_ms = conv_time_per_step(pipe, iml, imr)
+        conv_ms, conv_classes = conv_time_per_step(pipe, iml, imr)
         tflops = 2 * TC_GMACS_PER_PAIR * 1e9 / (conv_ms / 1e3) / 1e12
         half = pipe.eng.half
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::%s implicit GEMM, all conv/FC launches of one step)" % ("f16" if half else "tf32"),
@@ -325,6 +325,8 @@ def run_ours(args):
                 # conv_ms_serialized: all 213 conv launches back to back on ONE stream (no other pair to fill idle SMs);
                 # in the pipelined step the same FLOPs retire within ms_per_step, hence the in-step lower bound
                 "conv_ms_serialized": round(conv_ms, 3),
+                # each class issued alone back to back; compare tflops with `peak` and algorithmic_tb_per_s with hbm_peak
+                "by_class": conv_classes, "hbm_peak_tb_per_s": round(pk["hbm_gbs"] / 1e3, 3),
                 "achieved_in_step_lower_bound": round(2 * TC_GMACS_PER_PAIR * 1e9 / (ms_per_step / 1e3) / 1e12, 2)}
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_sample()
@@ -375,18 +377,42 @@ def conv_time_per_step(pipe, iml, imr):
     L = lib.load()
     st = lib.stream_ptr()
     tc = [(d, keep) for d, impl, keep in rec if impl == "tc"]
-    best = None
-    for _ in range(3):          # one event pair around the whole back-to-back sequence (PDL overlap as in the real step)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for d, _k in tc:
-            L.sb_conv2d_tc(ctypes.byref(d), st)
-        e.record()
-        torch.cuda.synchronize()
-        t = s.elapsed_time(e)
-        best = t if best is None else min(best, t)
-    return best
 
+    def seq_ms(descs):
+        """one event pair around a back-to-back sequence (PDL overlap as in the real step), best of 3"""
+        best = None
+        for _ in range(3):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for d in descs:
+                L.sb_conv2d_tc(ctypes.byref(d), st)
+            e.record()
+            torch.cuda.synchronize()
+            t = s.elapsed_time(e)
+            best = t if best is None else min(best, t)
+        return best
+
+    total = seq_ms([d for d, _k in tc])
+    # the same launches by what bounds them: big-M 3x3 convs (tensor pipe), big-M 1x1 convs with the residual
+    # epilogue (HBM: fp16 in + fp32 residual in + fp32 out + fp16 twin out), everything else (small M: layers 3-4,
+    # FC heads, 1x1 convs without residual -- L2 fill / latency)
+    classes = {"tensor: 3x3 convs, M >= 30000 px": [], "hbm: 1x1 + residual, M >= 30000 px": [], "other (small M / plain 1x1)": []}
+    for d, _k in tc:
+        M = d.N * d.Ho * d.Wo
+        key = ("tensor: 3x3 convs, M >= 30000 px" if d.kh == 3 and M >= 30000 else
+               "hbm: 1x1 + residual, M >= 30000 px" if d.residual and M >= 30000 else "other (small M / plain 1x1)")
+        classes[key].append(d)
+    by_class = []
+    for key, ds in classes.items():
+        if not ds:
+            continue
+        ms = seq_ms(ds)
+        fl = sum(2.0 * d.N * d.Ho * d.Wo * d.Cout * d.kh * d.kw * d.Cin for d in ds)
+        by = sum(d.N * d.Ho * d.Wo * (d.Cin * (2 if d.in_dtype == 1 else 4) + d.Cout *
+                                      ((4 if d.out else 0) + (2 if d.out16 else 0) + (4 if d.residual else 0))) for d in ds)
+        by_class.append({"class": key, "launches": len(ds), "ms": round(ms, 3), "tflops": round(fl / ms / 1e9, 1),
+                         "algorithmic_tb_per_s": round(by / ms / 1e9, 2)})
+    return total, by_class
 
 # ----------------------------------------------------------------------------------------------
 def _cpu_threads():

@@ -7,9 +7,9 @@
 //   * only the upper triangle of 64x64 tiles is computed (the reference computes
 //     the full square and never reads the lower half);
 //   * the greedy scan runs on the device, one 64-box chunk at a time: the chunk's
-//     diagonal tile is resolved sequentially from shared memory, then every kept
-//     row of the chunk is OR-ed into the running suppression words by one thread
-//     per 64-bit word (coalesced row reads, independent loads in flight);
+//     diagonal tile is resolved with warp shuffles, and both the tile and the
+//     chunk's suppression word (OR of that word over all boxes kept so far) are
+//     requested from L2 one chunk ahead of their use;
 //   * no cudaMalloc / cudaMemcpy / default-stream sync: workspace is caller-owned,
 //     everything is ordered on the caller's stream;
 //   * two box sets that share scores (left / right proposals) are reduced in
@@ -52,34 +52,68 @@ nms_mask_kernel(const float* __restrict__ boxes0, const float* __restrict__ boxe
     }
 }
 
-// One CTA, 256 threads per side.  keep_out receives ascending indices of boxes kept by
-// *every* side; at most max_out of them.
+// One CTA, 256 threads per side.  keep_out receives ascending indices of boxes kept by *every* side; at most
+// max_out of them.
+//
+// The scan is a chain of 64-box chunks, and each link needs two things from the mask in L2: the chunk's diagonal
+// tile, and the suppression word of the chunk = OR of word c over every box kept so far.  Both are requested one
+// chunk ahead, so a link costs max(resolve, one L2 round trip) instead of two round trips back to back:
+//   * thread j of a side owns chunk j: while chunk c is being resolved it gathers word c+1 of the rows chunk j
+//     kept (j < c), and the partial words are OR-reduced into shared memory;
+//   * warp 0 of the side holds, for the rows of chunk c, word c (the diagonal tile, resolved with shuffles as
+//     before) and word c+1: the boxes chunk c itself keeps are known only after the resolve, and their word c+1 is
+//     then already in registers ("carry").
 template <int NS>
 __global__ void __launch_bounds__(256 * NS)
 nms_reduce_kernel(const unsigned long long* __restrict__ mask0,
                   const unsigned long long* __restrict__ mask1, int n, int max_out,
                   int* __restrict__ keep_out, int* __restrict__ num_out) {
-    __shared__ unsigned long long remv[NS][kMaxWords];
-    __shared__ unsigned long long keepbits[NS];
+    __shared__ unsigned long long keepbits[NS][kMaxWords];   // per side: survivors of every resolved chunk
+    __shared__ unsigned long long colacc[NS][2];             // [c & 1]: OR of word c over the survivors of chunks < c-1... see below
     __shared__ int count;
-    const int side = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int side = threadIdx.x >> 8, t = threadIdx.x & 255, lane = t & 31;
     const unsigned long long* mask = side ? mask1 : mask0;
     const int cb = (n + kTile - 1) / kTile;
-    for (int w = t; w < kMaxWords; w += 256) remv[side][w] = 0;
+    if (t < 2) colacc[side][t] = 0;
     if (threadIdx.x == 0) count = 0;
+    // warp 0: rows lane and lane+32 of the current chunk: word c (d*) and word c+1 (e*)
+    unsigned long long d0 = 0, d1 = 0, e0 = 0, e1 = 0, carry = 0;
+    auto load_rows = [&](int c, unsigned long long& a0, unsigned long long& a1, unsigned long long& b0,
+                         unsigned long long& b1) {
+        const int csize = min(n - c * kTile, kTile);
+        const size_t r0 = (size_t)(c * kTile + lane) * cb, r1 = r0 + (size_t)32 * cb;
+        a0 = (lane < csize) ? mask[r0 + c] : 0ULL;
+        a1 = (lane + 32 < csize) ? mask[r1 + c] : 0ULL;
+        b0 = (lane < csize && c + 1 < cb) ? mask[r0 + c + 1] : 0ULL;
+        b1 = (lane + 32 < csize && c + 1 < cb) ? mask[r1 + c + 1] : 0ULL;
+    };
+    if (t < 32) load_rows(0, d0, d1, e0, e1);
     __syncthreads();
     for (int c = 0; c < cb; ++c) {
-        const int csize = min(n - c * kTile, kTile);
-        // resolve the chunk's 64x64 diagonal tile inside warp 0 of each side: lane l holds rows l and l+32 in
-        // registers and the sequential scan broadcasts row b with a shuffle (no shared-memory latency on the
-        // 64-step dependency chain)
+        // ---- requests for chunk c+1, in flight while chunk c is resolved
+        unsigned long long nd0 = 0, nd1 = 0, ne0 = 0, ne1 = 0, part = 0;
+        if (c + 1 < cb) {
+            if (t < 32) load_rows(c + 1, nd0, nd1, ne0, ne1);
+            if (t < c) {      // word c+1 of the rows chunk t kept
+                unsigned long long kb = keepbits[side][t];
+                const unsigned long long* col = mask + (size_t)t * kTile * cb + (c + 1);
+                while (kb) {
+                    unsigned long long v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {          // four independent loads per trip
+                        const int b = kb ? __ffsll((long long)kb) - 1 : -1;
+                        kb &= kb - 1;                       // (0 & anything) stays 0
+                        v[u] = b >= 0 ? col[(size_t)b * cb] : 0ULL;
+                    }
+                    part |= (v[0] | v[1]) | (v[2] | v[3]);
+                }
+            }
+        }
+        // ---- resolve chunk c inside warp 0 of each side
         if (t < 32) {
-            const int r0 = c * kTile + t, r1 = r0 + 32;
-            const unsigned long long d0 = (t < csize) ? mask[(size_t)r0 * cb + c] : 0ULL;
-            const unsigned long long d1 = (t + 32 < csize) ? mask[(size_t)r1 * cb + c] : 0ULL;
-            unsigned long long cur = remv[side][c], kb = 0;
+            const int csize = min(n - c * kTile, kTile);
             const unsigned long long valid = csize >= 64 ? ~0ULL : ((1ULL << csize) - 1ULL);
-            cur |= ~valid;
+            unsigned long long cur = colacc[side][c & 1] | carry | ~valid, kb = 0;
 #pragma unroll 8
             for (int b = 0; b < 32; ++b) {
                 const unsigned long long row = __shfl_sync(0xffffffffu, d0, b);
@@ -90,12 +124,22 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask0,
                 const unsigned long long row = __shfl_sync(0xffffffffu, d1, b);
                 if (!((cur >> (b + 32)) & 1ULL)) { kb |= 1ULL << (b + 32); cur |= row; }
             }
-            if (t == 0) keepbits[side] = kb;
+            // word c+1 of the rows this chunk keeps -> next chunk's carry (every lane gets the full OR)
+            unsigned long long mine = (((kb >> lane) & 1ULL) ? e0 : 0ULL) | (((kb >> (lane + 32)) & 1ULL) ? e1 : 0ULL);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, o);
+            carry = mine;
+            if (lane == 0) { keepbits[side][c] = kb; colacc[side][c & 1] = 0; }    // slot c&1 is reused for word c+2
+            d0 = nd0; d1 = nd1; e0 = ne0; e1 = ne1;
         }
+        // ---- OR-reduce the gathered partial words of chunk c+1 into colacc[(c+1)&1]
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part |= __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0 && part) atomicOr(&colacc[side][(c + 1) & 1], part);
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long both = keepbits[0];
-            if (NS == 2) both &= keepbits[NS - 1];
+            unsigned long long both = keepbits[0][c];
+            if (NS == 2) both &= keepbits[NS - 1][c];
             int cnt = count;
             while (both && cnt < max_out) {
                 int b = __ffsll((long long)both) - 1;
@@ -103,21 +147,6 @@ nms_reduce_kernel(const unsigned long long* __restrict__ mask0,
                 keep_out[cnt++] = c * kTile + b;
             }
             count = cnt;
-        }
-        {
-            // OR the rows of this side's kept boxes into the suppression words beyond chunk c
-            unsigned long long kb = keepbits[side];
-            for (int w = t; w < cb; w += 256) {
-                if (w <= c) continue;
-                unsigned long long acc = 0;
-                unsigned long long k2 = kb;
-                while (k2) {
-                    int b = __ffsll((long long)k2) - 1;
-                    k2 &= k2 - 1;
-                    acc |= mask[(size_t)(c * kTile + b) * cb + w];
-                }
-                remv[side][w] |= acc;
-            }
         }
         __syncthreads();
         if (count >= max_out) break;

@@ -325,3 +325,29 @@ def test_reference_module_interface(golden_dir):
     assert out[4].shape == (1, 300, 10) and out[5].shape == (300, 112) and out[6].shape == (300, 28)
     with pytest.raises(NotImplementedError):
         m.train()
+
+
+def test_latency_and_throughput_schedules_agree():
+    """The latency schedule (left/right chains of layers 3-4, RPN levels and the box head forked onto a second
+    stream; narrower tiles for the per-image chains) and the throughput schedule (one batched chain, no forks)
+    launch the same arithmetic: a conv output element is the same K-ordered tcgen05 accumulation whatever the tile
+    width, so features agree to rounding noise at most and the proposals are identical."""
+    H, W = 160, 320
+    left, right = synth_pair(H, W, 5, 9)
+    sd = OM.make_state_dict(3)
+    iml, imr = cu(torch.from_numpy(left)[None]), cu(torch.from_numpy(right)[None])
+    info = cu(torch.tensor([[float(H), float(W), 1.0]]))
+    outs = []
+    for lr in (True, False):
+        eng = E.StereoRCNNEngine(sd, "cuda", lr_streams=lr)
+        if not lr:
+            eng.rpn_streams = eng.head_streams = False
+        o = eng.forward(iml, imr, info, keep_features=True)
+        torch.cuda.synchronize()
+        outs.append(o)
+    a, b = outs
+    for k in ("p2", "p4", "p6", "c4", "c5"):
+        assert rel_err(a["feats"][k].cpu(), b["feats"][k].cpu()) < 1e-6, k
+    assert torch.equal(a["rois_left"], b["rois_left"]) and torch.equal(a["rois_right"], b["rois_right"])
+    for k in ("cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob"):
+        assert rel_err(a[k].cpu(), b[k].cpu()) < 1e-5, k
