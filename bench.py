@@ -98,7 +98,7 @@ class Pipeline(object):
         from stereo_rcnn_b200.synth import make_state_dict
         self.ops, self.dev = ops, device
         self.eng = engine.StereoRCNNEngine(make_state_dict(3), device, lr_streams=False if throughput else None)
-        if throughput:
+        if throughput and os.environ.get("SB_TP_FORKS", "0") == "0":
             self.eng.rpn_streams = self.eng.head_streams = False
         self.info = torch.tensor([[H_NET, W_NET, SCALE]], dtype=torch.float32, device=device)
         self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "1") != "0" else None
