@@ -115,9 +115,10 @@ int sb_dense_align(const float* im_left, const float* im_right, int H, int W,
 typedef struct {
     const float* in;        /* [N,H,W,in_ld] channels [0,Cin) used */
     const float* wgt;       /* [Cout][kh][kw][Cin] */
-    const float* scale;     /* [Cout] or NULL (folded frozen BN gamma/sqrt(var+eps)) */
-    const float* shift;     /* [Cout] or NULL (folded BN beta / conv bias) */
-    const float* residual;  /* [N,Ho,Wo,res_ld] or NULL: added before ReLU */
+    const float* scale;     /* [Cout] or NULL (folded frozen BN gamma/sqrt(var+eps)); 16-byte aligned for the tcgen05 path */
+    const float* shift;     /* [Cout] or NULL (folded BN beta / conv bias); 16-byte aligned for the tcgen05 path */
+    const float* residual;  /* [N,Ho,Wo,res_ld] or NULL: added before ReLU (tcgen05 path: 1x1 convs only -- conv3 of a
+                             * bottleneck; sb_conv2d_tc_supported() says no otherwise and the SIMT kernel takes it) */
     const float* up_src;    /* [N,UH,UW,Cout] or NULL: bilinear(align_corners) upsample to Ho x Wo, added */
     float* out;             /* out[n*out_n_stride + ho*out_h_stride + wo*out_w_stride + out_coff + c] */
     int N, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;

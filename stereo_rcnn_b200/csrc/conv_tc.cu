@@ -7,22 +7,26 @@
 //   D[M = output pixels, N = Cout] = sum over taps (r,s) and Cin chunks of
 //        A[(pixel shifted by tap), Cin chunk] * W[Cout, tap, Cin chunk]^T
 //
-//   * operands are fp32 in HBM (NHWC activations, [Cout][kh][kw][Cin] weights) and are fed to
-//     `tcgen05.mma.kind::tf32` unchanged (the tensor core reads the top 19 bits); accumulation
-//     is fp32 in TMEM.  The exact-fp32 SIMT kernel (conv_simt.cu) is the yardstick.
-//   * TMA moves every tile: weights through a 2-D map, activations through a 2-D map (1x1:
-//     pixels are rows of a flat [M, Cin] matrix) or a 4-D [C, W, H, N] map (3x3: an 8x16 pixel
-//     patch per tile; the tap shift is a coordinate offset and the hardware zero-fills the
-//     padding halo, so im2col never exists in memory).  128-byte swizzle, 1024-byte aligned
-//     stages, one 128-byte row (= 32 fp32 = BLOCK_K) per pixel per stage.
-//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA
-//     issuer (one elected lane) + TMEM allocator, warps 2..9 = epilogue (two warps per TMEM lane
-//     quarter, each taking half of the tile's columns).  Three mbarrier
-//     pipelines: smem full/empty (kStages deep), TMEM full/empty (two accumulator stages, so
-//     the epilogue of tile i overlaps the main loop of tile i+1).
-//   * fused epilogue straight out of TMEM (`tcgen05.ld.32x32b.x32`): folded frozen-BN
-//     scale/shift or bias, residual add, FPN bilinear (align_corners) upsample-add, ReLU,
-//     strided / channel-offset stores (RPN L/R concat, deconv scatter).
+//   * operands are fp16 in HBM by default (in_dtype 1: NHWC activations, [Cout][kh][kw][Cin] weights, both rounded
+//     to nearest once by their producer) and feed `tcgen05.mma.kind::f16`; the fp32 / `kind::tf32` mode (in_dtype 0,
+//     the tensor core reads the top 19 bits) is kept for comparison.  Accumulation is fp32 in TMEM either way; the
+//     exact-fp32 SIMT kernel (conv_simt.cu) is the yardstick.
+//   * TMA moves every operand tile: weights through a 2-D map, activations through a 2-D map (1x1: pixels are rows
+//     of a flat [M, Cin] matrix) or a 4-D [C, W, H, N] map (3x3: an 8x16 pixel patch per tile; the tap shift is a
+//     coordinate offset and the hardware zero-fills the padding halo, so im2col never exists in memory).  128-byte
+//     swizzle, 1024-byte aligned stages, one 128-byte row (64 fp16 / 32 fp32 = one K-step) per pixel per stage.
+//   * warp-specialised persistent CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane)
+//     + TMEM allocator, warps 2..9 = epilogue (two warps per TMEM lane quarter, each taking half of the tile's
+//     columns).  Three mbarrier pipelines: smem full/empty (4 stages of 48 KB for 256-wide tiles, 6 of 32 KB for
+//     128-wide ones -- the main loop is bound by bytes in flight, so nearly all shared memory is operand stages),
+//     TMEM full/empty (two accumulator stages: the epilogue of tile i overlaps the main loop of tile i+1).
+//   * fused epilogue out of TMEM (`tcgen05.ld.32x32b.x32`): folded frozen-BN scale/shift or bias, residual add
+//     (rows prefetched into registers across tile boundaries and into L2 with cp.async.bulk.prefetch two tiles
+//     ahead), FPN bilinear (align_corners) upsample-add, ReLU, fp32 and/or fp16 ("twin") stores with arbitrary
+//     n/h/w strides and channel offset (RPN L|R concat, deconv scatter).  See the epilogue's own comment block.
+//   * programmatic dependent launch: the prologue (barrier init, TMEM alloc, descriptor prefetch) overlaps the
+//     previous kernel's tail; dependents are released after the CTA's last MMAs.
+//   * optional per-CTA phase trace (sb_conv_trace) for tools/conv_trace.py.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
