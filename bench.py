@@ -139,6 +139,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # N ranks synthesise and pack the same weights on the host at start-up: do not let each of them spawn one
+        # CPU thread per core (has no effect on the timed, GPU-side region)
+        torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // world)))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from stereo_rcnn_b200 import ops
