@@ -47,12 +47,14 @@ def test_struct_layout_matches_c(so_path):
 
 
 def test_no_oracle_import_in_product():
-    """the product package must never import the oracle (parity would be void)"""
+    """the product package and the measurement tools must never import the oracle (parity would be void); only
+    tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU-baseline legs may"""
     bad = []
-    for dp, _, fs in os.walk(os.path.join(ROOT, "stereo_rcnn_b200")):
-        for f in fs:
-            if f.endswith(".py"):
-                src = open(os.path.join(dp, f)).read()
-                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
-                    bad.append(os.path.join(dp, f))
+    for top in ("stereo_rcnn_b200", "tools"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, top)):
+            for f in fs:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                        bad.append(os.path.join(dp, f))
     assert not bad, bad

@@ -40,7 +40,7 @@ def l2_err(a, b):
 
 # Tolerance of the composed forward (BASELINE.json: "within 1e-3 relative for FP32 feature/box tensors"):
 # relative L2 error < 1e-3 on every tensor; the max-norm relative error of a ~100-layer TF32 chain sits at
-# 0.3-1.1e-3 (measured, tools/err_report.py), so the max-norm bound is 1.5e-3.  The exact-fp32 SIMT path
+# 0.3-1.1e-3 (measured, tests/tools/err_report.py), so the max-norm bound is 1.5e-3.  The exact-fp32 SIMT path
 # (SB_CONV_IMPL=simt) is held to 2e-5.
 def close(a, b, impl):
     if impl == "simt":

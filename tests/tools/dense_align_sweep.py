@@ -12,7 +12,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 from oracle import ops as O  # noqa: E402
 from stereo_rcnn_b200 import ops  # noqa: E402
 from stereo_rcnn_b200.synth import DEMO_P2, DEMO_P3, gen_rois, synth_pair  # noqa: E402

@@ -5,7 +5,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 from oracle import model as OM  # noqa: E402
 from stereo_rcnn_b200 import engine as E  # noqa: E402
 from stereo_rcnn_b200.synth import make_state_dict, synth_pair  # noqa: E402
