@@ -88,6 +88,50 @@ def main():
     gold = {n: o.numpy() for n, o in zip(names, outs[:8])}
     np.savez_compressed(os.path.join(HERE, "forward_small.npz"), H=H, W=W, seed=11, shift=7,
                         weight_seed=3, **gold)
+    # ---- (5) proposal layer, TRAIN configuration (12000 / 2000, NMS 0.7) ----------------
+    rs = np.random.RandomState(17)
+    prob = rs.rand(1, A, 2).astype(np.float32)
+    bbox = (rs.randn(1, A, 6) * 0.3).astype(np.float32)
+    info = np.array([[160., 256., 1.0]], np.float32)
+    layer = ref.proposal_layer._ProposalLayer(cfg.FEAT_STRIDE[0], cfg.ANCHOR_RATIOS)
+    rl, rr = layer((torch.from_numpy(prob), torch.from_numpy(bbox), torch.from_numpy(info), "TRAIN", pshapes))
+    np.savez_compressed(os.path.join(HERE, "proposal_train.npz"), shapes=np.array(pshapes), cls_prob=prob,
+                        bbox_pred=bbox, im_info=info, rois_left=rl.numpy(), rois_right=rr.numpy())
+
+    # ---- (6) test-time decode: the reference's own script lines (test_net.py:138-212) -----
+    # executed from the file where it lies -- nothing is copied -- on synthetic head outputs
+    R = 96
+    rs = np.random.RandomState(23)
+    x1 = rs.rand(R) * 1500
+    y1 = rs.rand(R) * 400
+    rois_l = np.stack([np.zeros(R), x1, y1, x1 + 8 + rs.rand(R) * 400, y1 + 8 + rs.rand(R) * 180], 1).astype(np.float32)
+    rois_r = rois_l.copy()
+    rois_r[:, [1, 3]] -= (rs.rand(R, 1) * 60).astype(np.float32)
+
+    def softmax(z):
+        e = np.exp(z - z.max(1, keepdims=True))
+        return (e / e.sum(1, keepdims=True)).astype(np.float32)
+    inp = dict(rois_left=rois_l[None], rois_right=rois_r[None], cls_prob=softmax(rs.randn(R, 2))[None],
+               bbox_pred=(rs.randn(1, R, 12) * 0.8).astype(np.float32),
+               bbox_pred_dim=rs.randn(1, R, 10).astype(np.float32),
+               kpts_prob=softmax(rs.randn(R, 4 * cfg.KPTS_GRID) * 2), left_prob=softmax(rs.randn(R, cfg.KPTS_GRID) * 2),
+               right_prob=softmax(rs.randn(R, cfg.KPTS_GRID) * 2), im_info=np.array([[600., 1987., 1.6]], np.float32))
+    import time as _time
+    import types
+    src = open(os.path.join(ref_shim.REF, "test_net.py")).read().split("\n")
+    lo = next(i for i, l in enumerate(src) if l.strip() == "scores = cls_prob.data")
+    hi = next(i for i, l in enumerate(src) if l.strip() == "dim_orien = dim_orien.squeeze()")
+    block = "\n".join(l[4:] if l.startswith("    ") else l for l in src[lo:hi + 1])
+    ns = {k: torch.from_numpy(v) for k, v in inp.items()}
+    ns.update(torch=torch, cfg=cfg, time=_time, imdb=types.SimpleNamespace(_classes=("__background__", "Car")),
+              bbox_transform_inv=ref.bbox_transform.bbox_transform_inv, clip_boxes=ref.bbox_transform.clip_boxes,
+              kpts_transform_inv=ref.bbox_transform.kpts_transform_inv,
+              border_transform_inv=ref.bbox_transform.border_transform_inv)
+    exec(compile(block, "test_net.py[%d:%d]" % (lo + 1, hi + 1), "exec"), ns)
+    np.savez_compressed(os.path.join(HERE, "test_decode.npz"), ref_lines=np.array([lo + 1, hi + 1]),
+                        scores=ns["scores"].numpy(), pred_boxes_left=ns["pred_boxes_left"].numpy(),
+                        pred_boxes_right=ns["pred_boxes_right"].numpy(), pred_kpts=ns["pred_kpts"].numpy(),
+                        dim_orien=ns["dim_orien"].numpy(), **inp)
     print("goldens written to", HERE)
 
 

@@ -313,3 +313,20 @@ def test_class_nms_vs_oracle():
     np.testing.assert_array_equal(keep[:ref.size].cpu().numpy(), ref)
     keep, num = G.class_nms(cu(scores * 0), cu(boxes), 1, 0.05, 0.3)
     assert int(num[0]) == 0
+
+
+def test_test_decode_vs_reference_script_golden(golden_dir):
+    """sb_test_decode against the golden minted by executing test_net.py's own decode lines (tests/golden/
+    make_golden.py (6)): index-valued columns exact, boxes to the exp-ulp level (torch.exp vs sb_expf)"""
+    g = np.load(os.path.join(golden_dir, "test_decode.npz"))
+    pbl, pbr, do, pk = G.test_decode(cu(g["rois_left"][0]), cu(g["rois_right"][0]), cu(g["bbox_pred"][0]),
+                                     cu(g["bbox_pred_dim"][0]), cu(g["kpts_prob"]), cu(g["left_prob"]),
+                                     cu(g["right_prob"]), cu(g["im_info"][0]))
+    ref = O.test_decode(g["rois_left"][0], g["rois_right"][0], g["cls_prob"][0], g["bbox_pred"][0],
+                        g["bbox_pred_dim"][0], g["kpts_prob"], g["left_prob"], g["right_prob"], g["im_info"][0])
+    for a, b in zip((pbl, pbr, do, pk), ref[1:]):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)                      # bit-exact against the oracle
+    np.testing.assert_allclose(pbl.cpu().numpy(), g["pred_boxes_left"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(pbr.cpu().numpy(), g["pred_boxes_right"], rtol=0, atol=2e-4)
+    np.testing.assert_array_equal(do.cpu().numpy(), g["dim_orien"])
+    np.testing.assert_array_equal(pk.cpu().numpy(), g["pred_kpts"])

@@ -182,3 +182,32 @@ def test_forward_matches_reference(golden_dir):
     for n in ("cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob", "left_border_prob", "right_border_prob"):
         a = o[n].numpy().reshape(g[n].shape)
         np.testing.assert_allclose(a, g[n], rtol=1e-4, atol=1e-5, err_msg=n)
+
+
+def test_proposal_layer_train_config_matches_reference(golden_dir):
+    """cfg_key "TRAIN" (12000 pre-NMS / 2000 post-NMS, IoU 0.7) through the reference's own _ProposalLayer"""
+    g = _load(golden_dir, "proposal_train.npz")
+    rl, rr = ops.proposal_layer(g["cls_prob"], g["bbox_pred"], g["im_info"], "TRAIN", g["shapes"].tolist())
+    assert rl.shape == g["rois_left"].shape and rr.shape == g["rois_right"].shape
+    assert rl.shape[1] == 2000
+    same = np.all(np.abs(rl - g["rois_left"]) < 1e-3, axis=2) & np.all(np.abs(rr - g["rois_right"]) < 1e-3, axis=2)
+    assert same.mean() > 0.97, same.mean()
+    nz = np.abs(g["rois_left"][0, :, 1:]).sum(1) > 0             # zero-padded tail (fewer than 2000 survivors)
+    assert nz.sum() == (np.abs(rl[0, :, 1:]).sum(1) > 0).sum()
+
+
+def test_test_time_decode_matches_reference_script_lines(golden_dir):
+    """A12: the golden was produced by executing test_net.py's own decode lines (ref_lines) on synthetic head
+    outputs; the oracle's restatement must reproduce them (float division kpts_type quirk included)"""
+    g = _load(golden_dir, "test_decode.npz")
+    sc, pbl, pbr, do, pk = ops.test_decode(g["rois_left"][0], g["rois_right"][0], g["cls_prob"][0], g["bbox_pred"][0],
+                                           g["bbox_pred_dim"][0], g["kpts_prob"], g["left_prob"], g["right_prob"],
+                                           g["im_info"][0])
+    np.testing.assert_array_equal(sc, g["scores"])
+    for a, b, name in ((pbl, g["pred_boxes_left"], "boxes_left"), (pbr, g["pred_boxes_right"], "boxes_right"),
+                       (do, g["dim_orien"], "dim_orien"), (pk, g["pred_kpts"], "kpts")):
+        assert a.shape == b.shape, name
+        assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), (name, np.abs(a - b).max())
+    # integer-valued columns are exact: keypoint type = argmax / 28 as a float, and the argmax probability
+    np.testing.assert_array_equal(pk[:, 1], g["pred_kpts"][:, 1])
+    np.testing.assert_array_equal(pk[:, 2], g["pred_kpts"][:, 2])
