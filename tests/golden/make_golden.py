@@ -132,6 +132,26 @@ def main():
                         scores=ns["scores"].numpy(), pred_boxes_left=ns["pred_boxes_left"].numpy(),
                         pred_boxes_right=ns["pred_boxes_right"].numpy(), pred_kpts=ns["pred_kpts"].numpy(),
                         dim_orien=ns["dim_orien"].numpy(), **inp)
+
+    # ---- (7) per-class NMS: the reference's own script lines (test_net.py:234-259) on the decode outputs of (6) ----
+    # threshold / sort / gather are the reference's statements; `nms` is ref_shim's stand-in for the cffi extension
+    # (the C restatement of nms_cuda_kernel.cu, itself pinned to the compiled reference kernel on the GPU box)
+    lo2 = next(i for i, l in enumerate(src) if l.strip().startswith("inds = torch.nonzero(scores[:,j] > eval_thresh)"))
+    hi2 = next(i for i, l in enumerate(src) if i > lo2 and l.strip() == "cls_kpts = cls_kpts[keep]")
+    body = [l for l in src[lo2:hi2 + 1] if l.strip() and not l.strip().startswith("#")]
+    ind0 = len(body[0]) - len(body[0].lstrip())
+    ind1 = len(body[2]) - len(body[2].lstrip())          # body of the `if inds.numel() > 0:` block
+    block2 = "\n".join((l[ind1:] if (len(l) - len(l.lstrip())) >= ind1 else l[ind0:]) for l in body
+                       if not l.strip().startswith("if inds.numel()"))
+    ns2 = dict(torch=torch, cfg=cfg, j=1, eval_thresh=0.05, nms=sys.modules["model.nms.nms_wrapper"].nms, scores=ns["scores"],
+               pred_boxes_left=ns["pred_boxes_left"], pred_boxes_right=ns["pred_boxes_right"],
+               dim_orien=ns["dim_orien"], pred_kpts=ns["pred_kpts"])
+    exec(compile(block2, "test_net.py[%d:%d]" % (lo2 + 1, hi2 + 1), "exec"), ns2)
+    kept_rois = ns2["inds"][ns2["order"]][ns2["keep"]].numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "class_nms.npz"), ref_lines=np.array([lo2 + 1, hi2 + 1]),
+                        scores=ns["scores"].numpy(), pred_boxes_left=ns["pred_boxes_left"].numpy(), cls=1,
+                        score_thresh=0.05, nms_thresh=float(cfg.TEST.NMS), kept_rois=kept_rois,
+                        cls_dets_left=ns2["cls_dets_left"].numpy(), cls_kpts=ns2["cls_kpts"].numpy())
     print("goldens written to", HERE)
 
 

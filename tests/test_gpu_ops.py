@@ -330,3 +330,12 @@ def test_test_decode_vs_reference_script_golden(golden_dir):
     np.testing.assert_allclose(pbr.cpu().numpy(), g["pred_boxes_right"], rtol=0, atol=2e-4)
     np.testing.assert_array_equal(do.cpu().numpy(), g["dim_orien"])
     np.testing.assert_array_equal(pk.cpu().numpy(), g["pred_kpts"])
+
+
+def test_class_nms_vs_reference_script_golden(golden_dir):
+    """sb_class_nms against the golden minted by executing test_net.py:234-259 on the decode golden"""
+    g = np.load(os.path.join(golden_dir, "class_nms.npz"))
+    keep, num = G.class_nms(cu(g["scores"]), cu(g["pred_boxes_left"]), int(g["cls"]), float(g["score_thresh"]),
+                            float(g["nms_thresh"]))
+    assert int(num[0]) == g["kept_rois"].size
+    np.testing.assert_array_equal(keep[:g["kept_rois"].size].cpu().numpy(), g["kept_rois"])

@@ -211,3 +211,13 @@ def test_test_time_decode_matches_reference_script_lines(golden_dir):
     # integer-valued columns are exact: keypoint type = argmax / 28 as a float, and the argmax probability
     np.testing.assert_array_equal(pk[:, 1], g["pred_kpts"][:, 1])
     np.testing.assert_array_equal(pk[:, 2], g["pred_kpts"][:, 2])
+
+
+def test_per_class_nms_matches_reference_script_lines(golden_dir):
+    """A13: test_net.py:234-259 executed on the decode golden (threshold, descending sort, NMS 0.3, gather)"""
+    g = _load(golden_dir, "class_nms.npz")
+    keep = ops.per_class_nms(g["scores"], g["pred_boxes_left"], int(g["cls"]), float(g["score_thresh"]),
+                             float(g["nms_thresh"]))
+    np.testing.assert_array_equal(np.asarray(keep, np.int64), g["kept_rois"])
+    j = int(g["cls"])
+    np.testing.assert_array_equal(g["pred_boxes_left"][keep][:, 4 * j:4 * j + 4], g["cls_dets_left"][:, :4])
