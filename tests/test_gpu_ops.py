@@ -339,3 +339,16 @@ def test_class_nms_vs_reference_script_golden(golden_dir):
                             float(g["nms_thresh"]))
     assert int(num[0]) == g["kept_rois"].size
     np.testing.assert_array_equal(keep[:g["kept_rois"].size].cpu().numpy(), g["kept_rois"])
+
+
+def test_proposal_layer_train_golden_bit_exact(golden_dir):
+    """TRAIN configuration (12000 / 2000 / IoU 0.7; here pre_nms_top_n exceeds the 10 236 anchors of the small
+    pyramid, so every anchor is a candidate) against the oracle (bit-exact) and the reference's own output"""
+    g = np.load(os.path.join(golden_dir, "proposal_train.npz"))
+    shapes = g["shapes"].tolist()
+    rl, rr = G.proposal_layer(cu(g["cls_prob"]), cu(g["bbox_pred"]), cu(g["im_info"]), "TRAIN", shapes)
+    ol, orr = O.proposal_layer(g["cls_prob"], g["bbox_pred"], g["im_info"], "TRAIN", shapes)
+    np.testing.assert_array_equal(rl.cpu().numpy(), ol)
+    np.testing.assert_array_equal(rr.cpu().numpy(), orr)
+    np.testing.assert_allclose(rl.cpu().numpy(), g["rois_left"], rtol=1e-6, atol=2e-4)
+    np.testing.assert_allclose(rr.cpu().numpy(), g["rois_right"], rtol=1e-6, atol=2e-4)
