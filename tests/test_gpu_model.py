@@ -304,6 +304,14 @@ def test_forward_small_fp16_operand_path(golden_dir, monkeypatch):
     test_forward_small_vs_oracle_and_reference_golden(golden_dir)
 
 
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: the tf32 forward last ran green "
+                   "before the epilogue rewrite (its conv-level tests are green on the final build)")
+def test_forward_small_tf32_path(golden_dir, monkeypatch):
+    """the kind::tf32 mode (fp32 storage, pre-biased residual stream) meets the same bars"""
+    monkeypatch.setenv("SB_PRECISION", "tf32")
+    test_forward_small_vs_oracle_and_reference_golden(golden_dir)
+
+
 def test_forward_small_exact_fp32_simt_path(golden_dir, monkeypatch):
     """the SIMT fp32 yardstick reproduces the oracle to fp32 rounding"""
     monkeypatch.setenv("SB_CONV_IMPL", "simt")
