@@ -359,3 +359,33 @@ def test_latency_and_throughput_schedules_agree():
     assert torch.equal(a["rois_left"], b["rois_left"]) and torch.equal(a["rois_right"], b["rois_right"])
     for k in ("cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob"):
         assert rel_err(a[k].cpu(), b[k].cpu()) < 1e-5, k
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent; not yet executed on hardware")
+@pytest.mark.parametrize("half", [False, True])
+def test_conv_tc_store_modes_are_exact_transforms(half):
+    """out_mode 1 (store rounded to TF32) and 2 (store +0x1000 in the bit pattern), and res_biased (residual stored
+    pre-biased) are exact, deterministic transforms of the plain launch: same accumulators, same epilogue math"""
+    g = torch.Generator().manual_seed(77)
+    N, Ci, H, W, Co = 2, 256, 19, 33, 512
+    x = torch.randn(N, H, W, Ci, generator=g).cuda()
+    w = (torch.randn(Co, 1, 1, Ci, generator=g) / Ci ** 0.5).cuda()
+    if half:
+        x, w = x.half(), w.half()
+    sc, sh = (torch.rand(Co, generator=g) + 0.5).cuda(), torch.randn(Co, generator=g).cuda()
+    res = torch.randn(N, H, W, Co, generator=g).cuda()
+
+    def run(out_mode=G.EXACT, residual=None, res_biased=False):
+        out = torch.empty(N, H, W, Co, device="cuda")
+        d = G.conv_desc(x, w, out, Ci, Co, 1, 1, 1, 0, H, W, scale=sc, shift=sh, residual=residual, relu=True,
+                        out_mode=out_mode, res_biased=res_biased)
+        assert G.conv2d(d, "tc") == "tc"
+        torch.cuda.synchronize()
+        return out
+    y0 = run()
+    assert torch.equal(run(G.ROUND_TF32), G.round_tf32_(y0.clone()))
+    assert torch.equal(G.unbias(run(G.BIASED)), y0)
+    yr = run(residual=res)
+    res_b = (res.view(torch.int32) + 0x1000).view(torch.float32).contiguous()
+    assert torch.equal(run(residual=res_b, res_biased=True), yr)
+    assert torch.equal(G.unbias(run(G.BIASED, residual=res_b, res_biased=True)), yr)
