@@ -87,47 +87,6 @@ def make_inputs(rank):
     return left, right, (b, k, p), (DEMO_P2, DEMO_P3)
 
 
-class Pipeline(object):
-    """the call a user makes: images in -> detection record + refined disparities out"""
-
-    def __init__(self, device, throughput=False):
-        """throughput=True: the schedule for several pairs in flight -- no intra-pair stream forks (left/right
-        chains, RPN levels, box head): they shorten one pair's latency but cost SM time that other pairs can use"""
-        from stereo_rcnn_b200 import engine, ops, parallel
-        self.par = parallel
-        from stereo_rcnn_b200.synth import make_state_dict
-        self.ops, self.dev = ops, device
-        self.eng = engine.StereoRCNNEngine(make_state_dict(3), device, lr_streams=False if throughput else None)
-        if throughput and os.environ.get("SB_TP_FORKS", "0") == "0":
-            self.eng.rpn_streams = self.eng.head_streams = False
-        self.info = torch.tensor([[H_NET, W_NET, SCALE]], dtype=torch.float32, device=device)
-        self.side = torch.cuda.Stream(device=device) if os.environ.get("SB_SIDE_STREAM", "1") != "0" else None
-
-    def step(self, iml, imr, calib4, rois3d):
-        ops = self.ops
-        side_out = []
-
-        def fork_dense_align():
-            # dense_align depends only on the input pair and the (synthetic) poses: a parallel branch of the CUDA
-            # graph, forked where the main branch runs its small proposal kernels and most SMs are idle
-            main = torch.cuda.current_stream()
-            self.side.wait_stream(main)
-            with torch.cuda.stream(self.side):
-                side_out.extend(ops.dense_align(calib4, SCALE32, iml, imr, *rois3d))
-        o = self.eng.forward(iml, imr, self.info, before_proposals=fork_dense_align if self.side is not None else None)
-        pbl, pbr, dimo, pk = ops.test_decode(o["rois_left"][0], o["rois_right"][0], o["bbox_pred"][0],
-                                             o["dim_orien_pred"][0], o["kpts_prob"], o["left_border_prob"],
-                                             o["right_border_prob"], self.info[0])
-        keep, nkeep = ops.class_nms(o["cls_prob"][0], pbl, 1, 0.05, 0.3)
-        if self.side is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
-            st, dis = side_out
-        else:
-            st, dis = ops.dense_align(calib4, SCALE32, iml, imr, *rois3d)
-        rec = self.par.detection_record(o["cls_prob"][0], pbl, pbr, dimo, pk)   # [300, 33]
-        return rec, keep, nkeep, st, dis
-
-
 SCALE32 = float(np.float32(SCALE))
 
 
@@ -144,7 +103,8 @@ def run_ours(args):
         torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // world)))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from stereo_rcnn_b200 import ops
+    from stereo_rcnn_b200 import ops, parallel, pipeline
+    from stereo_rcnn_b200.synth import make_state_dict
     left, right, (b, k, p), (P2, P3) = make_inputs(rank)
     calib4 = ops.calib_vec(P2, P3)
     host_l = torch.from_numpy(left)[None].pin_memory()
@@ -156,20 +116,22 @@ def run_ours(args):
     use_graph = os.environ.get("SB_GRAPH", "1") != "0"
     if not use_graph:
         n_inflight = 1
-    pipe_lat = Pipeline(dev)                                            # one pair at a time: lowest latency
-    pipe = Pipeline(dev, throughput=True) if n_inflight > 1 else pipe_lat
+    sd = make_state_dict(3)
+    # the public end-to-end API of the package (stereo_rcnn_b200.pipeline): StereoPipeline.step is the call a user
+    # makes, GraphSlot is one in-flight step (own stream, fixed inputs, private workspaces, CUDA graph)
+    pipe_lat = pipeline.StereoPipeline(sd, dev, scale=SCALE)             # one pair at a time: lowest latency
+    pipe = pipeline.StereoPipeline(sd, dev, throughput=True, scale=SCALE) if n_inflight > 1 else pipe_lat
     copy_stream = torch.cuda.Stream(device=dev)
+    gather = parallel.RecordGather(world, rank, dev, dist, n_slots=n_inflight + 1, mode=args.gather)
 
-    class Slot(object):
-        """everything one in-flight pair owns: its stream, the CUDA graph of one step with fixed input buffers,
-        the pinned-host staging pair for the next H2D, and the host landing buffers of its results"""
+    class Slot(pipeline.GraphSlot):
+        """a GraphSlot plus the bench's host side: the pinned-host staging pair for the next H2D and the host
+        landing buffers of the slot's results"""
 
-        def __init__(self, pipe, own_stream):
-            self.pipe = pipe
-            self.stream = torch.cuda.Stream(device=dev) if own_stream else torch.cuda.current_stream()
-            self.iml, self.imr = iml.clone(), imr.clone()
-            self.gathered = torch.empty(world, N_ROIS, REC_COLS, device=dev) if world > 1 else None
-            self.host_rec = torch.empty(N_ROIS, REC_COLS).pin_memory()
+        def __init__(self, pipe, own_stream, index):
+            super().__init__(pipe, iml, imr, calib4, rois3d, own_stream=own_stream, use_graph=use_graph)
+            self.index = index
+            self.host_rec = torch.empty(world, N_ROIS, REC_COLS).pin_memory()
             self.host_dis = torch.empty(D_ALIGN).pin_memory()
             self.staging = [(torch.empty_like(iml), torch.empty_like(imr)) for _ in range(1 if own_stream else 2)]
             self.ready = [torch.cuda.Event() for _ in self.staging]
@@ -177,17 +139,6 @@ def run_ours(args):
             for ev in self.freed:
                 ev.record()
             self.k, self.primed = 0, False
-            self.runner = None
-            if use_graph:
-                # the ~170 launches of one step are captured once into a CUDA graph (no tracing compiler: the graph
-                # is the literal launch sequence of our kernels) and replayed; inputs live in fixed device buffers
-                from stereo_rcnn_b200.engine import GraphRunner
-                self.runner = GraphRunner(lambda a, c: self.pipe.step(a, c, calib4, rois3d), [self.iml, self.imr])
-
-        def run(self):
-            if use_graph:
-                return self.runner()
-            return self.pipe.step(self.iml, self.imr, calib4, rois3d)
 
         def prefetch(self, j):
             with torch.cuda.stream(copy_stream):
@@ -198,13 +149,11 @@ def run_ours(args):
 
         def step_resident(self):
             rec, keep, nkeep, st, dis = self.run()
-            if world > 1:
-                pipe.par.gather_records(rec, world, dist, out=self.gathered)
-            return rec, dis
+            return gather(self.index, rec[0]), dis[0]
 
         def step_e2e(self):
             """H2D of this slot's next pair (pinned host -> staging, copy stream) overlaps compute; every step still
-            moves its own 28.6 MB in and its record out inside the timed region"""
+            moves its own 28.6 MB in and its records out inside the timed region"""
             if use_graph:
                 nst = len(self.staging)
                 j = self.k % nst
@@ -213,24 +162,20 @@ def run_ours(args):
                     self.primed = True
                 cur = torch.cuda.current_stream()
                 cur.wait_event(self.ready[j])
-                self.iml.copy_(self.staging[j][0], non_blocking=True)   # device-to-device into the graph's fixed inputs
-                self.imr.copy_(self.staging[j][1], non_blocking=True)
+                self.load(*self.staging[j])              # device-to-device into the graph's fixed inputs
                 self.freed[j].record(cur)
-                self.prefetch((self.k + 1) % nst)                        # the next pair's H2D runs under this compute
+                self.prefetch((self.k + 1) % nst)         # the next pair's H2D runs under this compute
                 self.k += 1
-                rec, keep, nkeep, st, dis = self.runner()
             else:
-                a = host_l.to(dev, non_blocking=True)
-                c = host_r.to(dev, non_blocking=True)
-                rec, keep, nkeep, st, dis = self.pipe.step(a, c, calib4, rois3d)
-            if world > 1:
-                pipe.par.gather_records(rec, world, dist, out=self.gathered)
-            self.host_rec.copy_(rec, non_blocking=True)
-            self.host_dis.copy_(dis, non_blocking=True)
-            return rec, dis
+                self.load(host_l, host_r)
+            rec, keep, nkeep, st, dis = self.run()
+            g = gather(self.index, rec[0])
+            self.host_rec.copy_(g, non_blocking=True)
+            self.host_dis.copy_(dis[0], non_blocking=True)
+            return g, dis[0]
 
-    lat_slot = Slot(pipe_lat, False)
-    slots = [Slot(pipe, True) for _ in range(n_inflight)] if n_inflight > 1 else [lat_slot]
+    lat_slot = Slot(pipe_lat, False, n_inflight if n_inflight > 1 else 0)
+    slots = [Slot(pipe, True, i) for i in range(n_inflight)] if n_inflight > 1 else [lat_slot]
     host_rec, host_dis = slots[0].host_rec, slots[0].host_dis
 
     def timed(fn, steps, warmup):
@@ -251,7 +196,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        return pipe.par.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), dev, world, dist)
+        return parallel.max_over_ranks(sum(s.elapsed_time(e) for s, e in ev), dev, world, dist)
 
     def timed_pipelined(method, steps, warmup):
         """n_inflight independent pairs in flight, each on its own stream (a pair's proposal / NMS stages leave most
@@ -284,7 +229,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        return pipe.par.max_over_ranks(s.elapsed_time(e), dev, world, dist)
+        return parallel.max_over_ranks(s.elapsed_time(e), dev, world, dist)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -304,6 +249,19 @@ def run_ours(args):
                   "l2": "256 MB flush between timed iterations"}
         total_ms = timed_pipelined("step_resident", args.steps, W + n_inflight)
         e2e_ms = timed_pipelined("step_e2e", args.steps, W + n_inflight)
+    # the exchange step alone (records already packed): device time of one gather per step, max over ranks
+    gather_ms = None
+    if world > 1:
+        rec0 = slots[0].outputs[0][0]
+        gather_ms = timed(lambda: gather(slots[0].index, rec0), args.steps, W) / args.steps
+    # every in-flight slot must have produced the result of the one-pair-at-a-time run on the same input: the
+    # schedules differ only in tile widths / stream forks, proposals are index-exact and records agree to rounding
+    torch.cuda.synchronize()
+    ref_rec = lat_slot.outputs[0][0]
+    checks = []
+    for sl in slots:
+        r_ = sl.outputs[0][0]
+        checks.append(float((r_ - ref_rec).abs().max() / ref_rec.abs().max()))
     sampler.stop_flag = True
     ms_per_step = total_ms / args.steps
     value = world * args.steps / (total_ms / 1e3)
@@ -312,6 +270,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live with CUDA events ----
     roof = None
     cpu_base = None
+    parity = None
     if rank == 0:
         pk = peaks()
         conv_ms, conv_classes = conv_time_per_step(pipe, iml, imr)
@@ -320,19 +279,19 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::%s implicit GEMM, all conv/FC launches of one step)" % ("f16" if half else "tf32"),
                 "achieved": round(tflops, 2), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": round(tflops / pk["bf16_tflops_sustained"], 4),
-                # dram__bytes_read+write summed over the 213 conv launches of one step, ncu capture of this same
-                # command (profiles/r01b_conv_dram.md); algorithmic FLOPs per step = 2 * 0.978 TMAC
+                # dram__bytes_read+write summed over the conv launches of one step, ncu capture of this same
+                # command (profiles/); algorithmic FLOPs per step = 2 * 0.978 TMAC
                 "traffic": CONV_DRAM_BYTES_PER_STEP if half else None,
                 "traffic_unit": "bytes per step (all conv launches)",
                 "peak_source": pk["src"] + " cuBLAS bf16 sustained" + ("" if half else " (kind::tf32 issues at half that rate)"),
-                # conv_ms_serialized: all 213 conv launches back to back on ONE stream (no other pair to fill idle SMs);
+                # conv_ms_serialized: all conv launches back to back on ONE stream (no other pair to fill idle SMs);
                 # in the pipelined step the same FLOPs retire within ms_per_step, hence the in-step lower bound
                 "conv_ms_serialized": round(conv_ms, 3),
                 # each class issued alone back to back; compare tflops with `peak` and algorithmic_tb_per_s with hbm_peak
                 "by_class": conv_classes, "hbm_peak_tb_per_s": round(pk["hbm_gbs"] / 1e3, 3),
                 "achieved_in_step_lower_bound": round(2 * TC_GMACS_PER_PAIR * 1e9 / (ms_per_step / 1e3) / 1e12, 2)}
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline_sample()
+            cpu_base, parity = cpu_baseline_sample(pipe_lat)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -351,18 +310,25 @@ def run_ours(args):
                           "through the 126 MB L2; steps of the %d in-flight pairs overlap, so no flush between them "
                           "(single_stream: flushed)" % n_inflight),
                    "inflight": n_inflight, "schedule": "throughput: %d independent batch-1 pairs in flight, one stream + CUDA "
-                   "graph each, no intra-pair forks" % n_inflight if n_inflight > 1 else "latency (one pair in flight)",
-                   "cuda_graph": use_graph, "parallelism": "dp%d (1 pair/rank)" % world},
+                   "graph + private workspaces each, no intra-pair forks" % n_inflight if n_inflight > 1 else "latency (one pair in flight)",
+                   "api": "stereo_rcnn_b200.pipeline.StereoPipeline.step via pipeline.GraphSlot",
+                   "cuda_graph": use_graph, "parallelism": "dp%d (1 pair/rank)" % world,
+                   "gather": gather.describe()},
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s",
                 "h2d_bytes_per_step": int(host_l.numel() * 4 * 2),
                 "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},
         "gpu_launches": int(launches) * args.steps,
+        "inflight_vs_single_max_rel_diff": [round(c, 9) for c in checks],
         "clocks": sampler.summary(), "roofline": roof,
     }
+    if gather_ms is not None:
+        out["gather_ms_per_step"] = round(gather_ms, 4)
     if single is not None:
         out["single_stream"] = single
     if cpu_base is not None:
         out["cpu_baseline"] = cpu_base
+    if parity is not None:
+        out["parity"] = parity
     print(json.dumps(out))
 
 
@@ -375,7 +341,7 @@ def conv_time_per_step(pipe, iml, imr):
     from stereo_rcnn_b200 import lib
     eng = pipe.eng
     eng.record = []
-    eng.forward(iml, imr, pipe.info)
+    eng.forward(iml, imr, pipe.im_info(1, iml.shape[2], iml.shape[3]))
     rec, eng.record = eng.record, None
     L = lib.load()
     st = lib.stream_ptr()
@@ -437,9 +403,9 @@ def _cpu_threads():
     return best
 
 
-def cpu_port_step(sd, left, right, crop_w, rois3d, calib):
+def cpu_port_step(sd, left, right, crop_w, rois3d, calib, want_outputs=False):
     """one pass of the hot path on the CPU port of the reference (oracle): forward + decode + NMS + dense_align
-    on a width-`crop_w` crop of the pair; returns seconds"""
+    on a width-`crop_w` crop of the pair; returns seconds (and the oracle's tensors if asked)"""
     from oracle import model as OM
     from oracle import ops as O
     iml = torch.from_numpy(left[:, :, :crop_w].copy())[None]
@@ -453,7 +419,46 @@ def cpu_port_step(sd, left, right, crop_w, rois3d, calib):
     O.per_class_nms(dec[0], dec[1], 1)
     b, k, p = rois3d
     O.dense_align(calib, SCALE32, left, right, b, k, p)
-    return time.time() - t
+    sec = time.time() - t
+    return (sec, o, (iml, imr, info)) if want_outputs else sec
+
+
+def parity_report(eng, o, iml, imr, info):
+    """the GPU forward against the oracle's tensors of the SAME pair at the benchmarked size and dtype: per tensor
+    (relative L2 error, max-norm relative error).  Heads are evaluated on the oracle's RoIs (identical inputs); the
+    end-to-end proposal overlap says how many of the oracle's 300 proposals the GPU's own RPN scores reproduce."""
+    from stereo_rcnn_b200 import ops
+
+    def err(a, b_):
+        a, b_ = np.asarray(a, np.float64), np.asarray(b_, np.float64)
+        return [float("%.3g" % (np.linalg.norm(a - b_) / max(np.linalg.norm(b_), 1e-30))),
+                float("%.3g" % (np.abs(a - b_).max() / max(np.abs(b_).max(), 1e-30)))]
+    dev = eng.device
+    r = eng.forward(iml.to(dev), imr.to(dev), info.to(dev), keep_features=True)
+    torch.cuda.synchronize()
+    rep = {}
+    for k in ("c2", "c3", "c4", "c5", "p2", "p3", "p4", "p5", "p6"):
+        got = r["feats"][k].float().permute(0, 3, 1, 2).cpu().numpy()
+        el, er = err(got[0:1], o["left"][k].numpy()), err(got[1:2], o["right"][k].numpy())
+        rep[k] = [max(el[0], er[0]), max(el[1], er[1])]
+    for k in ("rpn_cls_prob", "rpn_bbox_pred"):
+        rep[k] = err(r[k].cpu().numpy(), o[k].numpy())
+    a = {tuple(np.round(x, 1)) for x in r["rois_left"][0].cpu().numpy()}
+    b_ = {tuple(np.round(x, 1)) for x in o["rois_left"][0].numpy()}
+    rl, rr = ops.proposal_layer(o["rpn_cls_prob"].to(dev), o["rpn_bbox_pred"].to(dev), info.to(dev), "TEST", o["rpn_shapes"])
+    exact = bool(np.array_equal(rl.cpu().numpy(), o["rois_left"].numpy()) and
+                 np.array_equal(rr.cpu().numpy(), o["rois_right"].numpy()))
+    h = eng.heads(r["feats_raw"], 1, rl.view(-1, 5), rr.view(-1, 5), float(iml.shape[2]))
+    torch.cuda.synchronize()
+    for k in ("pooled_box", "pooled_kpts"):
+        rep[k] = err(h[k].float().permute(0, 3, 1, 2).cpu().numpy(), o[k].numpy())
+    for k in ("fc7", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob", "left_border_prob", "right_border_prob"):
+        rep[k] = err(h[k].cpu().numpy().reshape(o[k].shape), o[k].numpy())
+    return {"vs": "CPU oracle (fp32) on the same pair, %dx%d, dtype %s" % (iml.shape[2], iml.shape[3], eng.precision),
+            "format": "[relative L2, max-norm relative] per tensor",
+            "tensors": rep, "worst_l2": max(v[0] for v in rep.values()), "worst_max_norm": max(v[1] for v in rep.values()),
+            "proposals_bit_exact_on_identical_inputs": exact,
+            "end_to_end_proposal_overlap": round(len(a & b_) / float(len(b_)), 4)}
 
 
 def pick_crop(threads):
@@ -472,17 +477,28 @@ def pick_crop(threads):
             return wcrop, frac
 
 
-def cpu_baseline_sample():
+def cpu_baseline_sample(pipe=None, passes=3):
+    """reported CPU baseline (kind "port": the oracle, all host threads): 1 warm-up + `passes` timed passes, mean;
+    the oracle's tensors of the last pass double as the parity reference for the GPU forward (same pair, same size)"""
     from oracle import ops as O
     from stereo_rcnn_b200.synth import make_state_dict
     threads = _cpu_threads()
     left, right, rois3d, (P2, P3) = make_inputs(0)
     wcrop, frac = pick_crop(threads)
     sd = make_state_dict(3)
-    sec = cpu_port_step(sd, left, right, wcrop, rois3d, O.calib_vec(P2, P3))
-    return {"value": round((wcrop / W_NET) / sec, 5), "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": "1 pass of the oracle (CPU port of the reference forward + decode + NMS + dense_align D=%d) on a "
-                      "600x%d crop of the pair (%.3f of the pixels), scaled to full pairs" % (D_ALIGN, wcrop, wcrop / W_NET)}
+    calib = O.calib_vec(P2, P3)
+    cpu_port_step(sd, left, right, wcrop, rois3d, calib)
+    secs = []
+    for _ in range(passes):
+        sec, o, ins = cpu_port_step(sd, left, right, wcrop, rois3d, calib, want_outputs=True)
+        secs.append(sec)
+    sec = sum(secs) / len(secs)
+    base = {"value": round((wcrop / W_NET) / sec, 5), "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "mean of %d passes (after 1 warm-up; min %.2f s, max %.2f s) of the oracle (CPU port of the reference "
+                      "forward + decode + NMS + dense_align D=%d) on a 600x%d crop of the pair (%.3f of the pixels), scaled "
+                      "to full pairs" % (passes, min(secs), max(secs), D_ALIGN, wcrop, wcrop / W_NET)}
+    parity = parity_report(pipe.eng, o, *ins) if pipe is not None else None
+    return base, parity
 
 
 def run_reference(args):
@@ -524,6 +540,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default=None, choices=[None, "peer", "nccl"],
+                    help="record exchange at N>1: own peer-memory kernels (default) or ncclAllGather")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("SB_INFLIGHT", "3")),
                     help="independent pairs in flight per GPU (each batch-1, own stream + CUDA graph)")
     args = ap.parse_args()

@@ -57,9 +57,10 @@ int sb_nms_mask(const float* dets, int n, float thresh, uint64_t* mask, sb_strea
 int sb_roi_align_forward(const float* features, int N, int C, int H, int W,
                          const float* rois, int R, int ah, int aw, float spatial_scale,
                          float* out, sb_stream_t stream);
-/* bottom_grad (N x C x H x W) must be zero-filled by the caller, as in the reference;
- * accumulation is deterministic (segmented by RoI tap, no float atomics ordering races
- * across launches: atomics are used, order-insensitive to 1 ulp)                  */
+/* bottom_grad (N x C x H x W) must be zero-filled by the caller, as in the reference.
+ * Like the reference kernel (roi_align_kernel.cu:94-143) the scatter uses four float
+ * atomicAdds per tap: the summation ORDER is not deterministic, results agree with the
+ * reference launcher to 1e-4 relative (tests/test_gpu_ops.py), not bit for bit.        */
 int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W,
                           const float* rois, int R, int ah, int aw, float spatial_scale,
                           float* bottom_grad, sb_stream_t stream);
@@ -184,15 +185,50 @@ int sb_test_decode(const float* rois_left, const float* rois_right, const float*
                    const float* right_prob, const float* im_info, int R, int n_classes, int grid,
                    float* pred_boxes_left, float* pred_boxes_right, float* dim_orien_out,
                    float* pred_kpts, sb_stream_t stream);
+/* the same decode that also emits the per-image detection record which ranks all-gather (the result
+ * packing of test_net.py:233-330): record[r] = [cls_prob nc | boxes_left 4nc | boxes_right 4nc | dim_orien 5nc |
+ * kpts 5], row pitch record_ld >= 15*nc + 5 floats                                                           */
+int sb_test_decode_record(const float* rois_left, const float* rois_right, const float* cls_prob,
+                          const float* bbox_pred, const float* dim_orien, const float* kpts_prob,
+                          const float* left_prob, const float* right_prob, const float* im_info, int R,
+                          int n_classes, int grid, float* pred_boxes_left, float* pred_boxes_right,
+                          float* dim_orien_out, float* pred_kpts, float* record, int record_ld,
+                          sb_stream_t stream);
 /* per-class detection NMS (test_net.py:233-259), one image: scores [R,nc], boxes [R,4nc] (decoded left
  * boxes); keeps RoIs with score[:,cls] > score_thresh, sorted by score, NMS(nms_thresh); keep[] (>= R
  * ints) receives RoI indices in kept order, num_out the count.  R <= 512.                          */
 int sb_class_nms(const float* scores, const float* boxes, int R, int n_classes, int cls,
                  float score_thresh, float nms_thresh, int* keep, int* num_out, sb_stream_t stream);
+/* input pipeline (lib/model/utils/blob.py:44-64 prep_im_for_blob + demo.py:124-128): uint8 HWC image (BGR, or RGB
+ * with rgb_input = 1 as scipy's imread returns it, demo.py:106) -> fp32 (pixel - cfg.PIXEL_MEANS) ->
+ * cv2.resize(fx = fy = scale, INTER_LINEAR) -> out [3, Ho, Wo] CHW, (Ho, Wo) from sb_prep_image_size            */
+int sb_prep_image_size(int H, int W, double scale, int* Ho, int* Wo);
+int sb_prep_image(const uint8_t* img, int H, int W, double scale, int rgb_input, float* out, sb_stream_t stream);
 /* L2 flush helper for benchmarks: writes `bytes` of scratch */
 int sb_fill(float* p, size_t n, float v, sb_stream_t stream);
 /* number of kernel launches issued by this library since load (bench "gpu_launches") */
 unsigned long long sb_launch_count(void);
+
+/* ------------------------------------------------- record all-gather over peer memory ----
+ * The path's only exchange: every rank's fixed-size detection record ([300, 15nc+5] fp32, ~40 KB) to every rank of
+ * one NVSwitch box.  Each rank owns a mailbox (sb_peer_alloc), exports it with CUDA IPC (sb_ipc_export, 64-byte
+ * handle exchanged by the host's control plane) and maps its peers' (sb_ipc_import).  sb_peer_put_record stores the
+ * local record into every mailbox (posted 128-bit NVLink writes + system-scope release of a sequence flag);
+ * sb_peer_wait_records acquires the world's flags for the same step in the local mailbox and copies the records to
+ * gathered[world][rec_floats].  Step counters live on the device: both calls are CUDA-graph capturable.  A peer
+ * that never delivers sets *err_flag (device int) to 1 + its rank after timeout_s instead of hanging the GPU.
+ * Replaces torch.distributed.all_gather / ncclAllGather on the data path; mailboxes[] is a HOST array of the
+ * `world` device pointers (own allocation at index `rank`).                                                  */
+size_t sb_peer_mailbox_bytes(int n_slots, int world, int rec_floats);
+int sb_peer_alloc(size_t bytes, void** ptr);
+int sb_peer_free(void* ptr);
+int sb_ipc_export(void* ptr, void* handle64);
+int sb_ipc_import(const void* handle64, void** ptr);
+int sb_ipc_close(void* ptr);
+int sb_peer_put_record(const float* rec, void* const* mailboxes, int n_slots, int world, int rec_floats,
+                       int rank, int slot, sb_stream_t stream);
+int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, float* gathered,
+                         int* err_flag, double timeout_s, sb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -342,3 +342,42 @@ def upsample2x(im):
     out = np.empty((C, 2 * H, 2 * W), np.float32)
     lib().oracle_upsample2x(_p(im), C, H, W, _p(out))
     return out
+
+
+# --------------------------------------------------------------------------
+# input pipeline (SURVEY 8f-3): prep_im_for_blob (lib/model/utils/blob.py:44-64) = BGR - PIXEL_MEANS (fp32), then
+# cv2.resize(fx=fy=scale, INTER_LINEAR), then HWC -> CHW (demo.py:124-128, roibatchLoader.py:111-113).
+# OpenCV (third-party, unpinned by the reference; 4.13 in this image) resizes float images separably: for each
+# output column dx, x = (dx+0.5)/scale - 0.5 in fp64, sx = floor(x), weight = float(x - sx), clamped to the image; a
+# horizontal pass a0*S[sx] + a1*S[sx+1] on the two source rows, then the vertical pass b0*row0 + b1*row1, in fp32.
+# Pinned empirically against cv2.resize of this image (tests/golden/make_golden.py (8)): <= 2 ulp at any scale
+# (cv2's SIMD path contracts some multiply-adds); computing the coordinate in fp32 instead is off by 1e-4 relative.
+# --------------------------------------------------------------------------
+PIXEL_MEANS = np.array([102.9801, 115.9465, 122.7717], np.float64)       # config.py:170 (BGR)
+
+
+def _resize_axis(n_src, scale):
+    n_dst = int(np.rint(n_src * scale))                 # cv::saturate_cast<int>(ssize * inv_scale) = cvRound
+    inv = 1.0 / float(scale)
+    x = (np.arange(n_dst, dtype=np.float64) + 0.5) * inv - 0.5
+    s = np.floor(x).astype(np.int64)
+    f = (x - s).astype(np.float32)
+    lo = s < 0
+    f[lo], s[lo] = 0.0, 0
+    hi = s >= n_src - 1
+    f[hi], s[hi] = 0.0, n_src - 1
+    s1 = np.minimum(s + 1, n_src - 1)
+    return n_dst, s, s1, (np.float32(1.0) - f).astype(np.float32), f
+
+
+def prep_image(bgr_u8, scale):
+    """[H,W,3] uint8 BGR -> [3, round(H*scale), round(W*scale)] fp32 network input (blob.py:44-64 + HWC->CHW)"""
+    # `img.astype(np.float32); img -= pixel_means` (float64 means): computed in fp64, stored as fp32
+    im = (bgr_u8.astype(np.float32).astype(np.float64) - PIXEL_MEANS).astype(np.float32)
+    H, W = im.shape[:2]
+    Ho, y0, y1, b0, b1 = _resize_axis(H, scale)
+    Wo, x0, x1, a0, a1 = _resize_axis(W, scale)
+    rows = (im[:, x0, :] * a0[None, :, None]).astype(np.float32) + (im[:, x1, :] * a1[None, :, None]).astype(np.float32)
+    rows = rows.astype(np.float32)
+    out = (rows[y0] * b0[:, None, None]).astype(np.float32) + (rows[y1] * b1[:, None, None]).astype(np.float32)
+    return np.ascontiguousarray(out.astype(np.float32).transpose(2, 0, 1))

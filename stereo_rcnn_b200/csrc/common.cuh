@@ -20,6 +20,25 @@ static inline cudaStream_t sb_cs(sb_stream_t s) { return (cudaStream_t)s; }
 
 static inline int sb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-device caches (function attributes and device properties belong to one device context; a process may drive
+// several GPUs).  Races between host threads are benign: every writer stores the same value.
+constexpr int kSbMaxDevices = 64;
+static inline int sb_cur_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= kSbMaxDevices) ? 0 : d;
+}
+static inline int sb_num_sms() {
+    static int sms[kSbMaxDevices] = {0};
+    const int d = sb_cur_device();
+    if (!sms[d]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+        sms[d] = n > 0 ? n : 148;
+    }
+    return sms[d];
+}
+
 // Deterministic expf, bit-identical to oracle/csrc/oracle_ops.c:sb_expf (every step is a
 // single IEEE operation: rintf, fmaf, integer scale).  Replaces torch.exp of
 // lib/model/rpn/bbox_transform.py:93-94 so that decoded boxes -- and therefore NMS keep

@@ -706,7 +706,8 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
     constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + epi_smem(EW);
     static_assert(smem * (EW == 4 ? 2 : 1) <= 227 * 1024, "smem budget");
     constexpr int kNumThreads = 64 + 32 * EW;
-    static bool attr = false;
+    static bool attr_done[kSbMaxDevices] = {false};
+    bool& attr = attr_done[sb_cur_device()];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, ST, RES, UP, IN16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess && EW == 4)
@@ -714,13 +715,7 @@ int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cu
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = sb_num_sms();
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     int slots = num_sms * (EW == 4 ? 2 : 1);
     if (p.d.max_ctas > 0 && p.d.max_ctas < slots) slots = p.d.max_ctas;
@@ -837,13 +832,7 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     p.tiles_w = (d->W + TW - 1) / TW;
     p.tiles_h = (d->H + TH - 1) / TH;
     p.num_m_tiles = p.patch ? d->N * p.tiles_h * p.tiles_w : (int)((p.M + BLOCK_M - 1) / BLOCK_M);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    const int sms = sb_num_sms();
     int BN = pick_block_n(d->Cout, p.num_m_tiles, sms);
     if (d->residual && BN == 256) BN = 128;   // residual layers are HBM-bound; the 256-wide residual epilogue spills
     // "small" variant (128x128 tiles, half the shared memory, two CTAs per SM): measured slower than the

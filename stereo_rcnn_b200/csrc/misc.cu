@@ -10,7 +10,7 @@ extern "C" unsigned long long sb_launch_count(void) { return g_sb_launches; }
 extern "C" int sb_version(void) { return 100; }
 extern "C" int sb_device_cc(void) {
     cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) return -1;
+    if (cudaGetDeviceProperties(&p, sb_cur_device()) != cudaSuccess) return -1;
     return p.major * 10 + p.minor;
 }
 
@@ -235,7 +235,8 @@ test_decode_kernel(const float* __restrict__ rois_l, const float* __restrict__ r
                    const float* __restrict__ kpts_prob, const float* __restrict__ left_prob,
                    const float* __restrict__ right_prob, const float* __restrict__ im_info, int R, int nc,
                    int grid, float* __restrict__ pbl, float* __restrict__ pbr, float* __restrict__ dimo,
-                   float* __restrict__ pkpts) {
+                   float* __restrict__ pkpts, const float* __restrict__ cls_prob, float* __restrict__ record,
+                   int rec_ld) {
     const int r = blockIdx.x * 128 + threadIdx.x;
     if (r >= R) return;
     const float stds[4] = {0.1f, 0.1f, 0.2f, 0.2f};           // cfg.TRAIN.BBOX_NORMALIZE_STDS/MEANS
@@ -279,6 +280,16 @@ test_decode_kernel(const float* __restrict__ rois_l, const float* __restrict__ r
     const float pr = __fadd_rn(__fdiv_rn(__fmul_rn((float)rd, width), g), bl.x);
     float* o = pkpts + (size_t)r * 5;
     o[0] = __fdiv_rn(pk, sc); o[1] = ktype; o[2] = km; o[3] = __fdiv_rn(pl, sc); o[4] = __fdiv_rn(pr, sc);
+    if (record) {
+        // the per-image detection record that is all-gathered across ranks: one row per RoI,
+        // [scores nc | boxes_left 4nc | boxes_right 4nc | dim_orien 5nc | kpts 5], emitted here instead of a torch.cat
+        float* q = record + (size_t)r * rec_ld;
+        for (int j = 0; j < nc; ++j) *q++ = cls_prob[(size_t)r * nc + j];
+        for (int j = 0; j < 4 * nc; ++j) *q++ = pbl[(size_t)r * 4 * nc + j];
+        for (int j = 0; j < 4 * nc; ++j) *q++ = pbr[(size_t)r * 4 * nc + j];
+        for (int j = 0; j < 5 * nc; ++j) *q++ = dimo[(size_t)r * 5 * nc + j];
+        for (int j = 0; j < 5; ++j) *q++ = o[j];
+    }
 }
 
 
@@ -351,7 +362,61 @@ class_nms_kernel(const float* __restrict__ scores, const float* __restrict__ box
     }
 }
 
+// Input pipeline: prep_im_for_blob (lib/model/utils/blob.py:44-64) + HWC->CHW (demo.py:124-128):
+// uint8 BGR image -> fp32 (pixel - PIXEL_MEANS) -> cv2.resize(fx=fy=scale, INTER_LINEAR) -> [3,Ho,Wo].
+// OpenCV's separable fp32 bilinear restated: source coordinate (d+0.5)/scale-0.5 and its fraction in fp64, the
+// horizontal pass on the two source rows first, then the vertical pass, one rounding per multiply / add.
+struct ResizeTap { int i0, i1; float w0, w1; };
+__device__ __forceinline__ ResizeTap resize_tap(int d, int n_src, double inv) {
+    const double x = ((double)d + 0.5) * inv - 0.5;
+    int s = (int)floor(x);
+    float f = (float)(x - (double)s);
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n_src - 1) { f = 0.f; s = n_src - 1; }
+    ResizeTap t;
+    t.i0 = s; t.i1 = min(s + 1, n_src - 1);
+    t.w0 = __fsub_rn(1.0f, f); t.w1 = f;
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+prep_image_kernel(const uint8_t* __restrict__ img, int H, int W, double inv, int rgb, float* __restrict__ out,
+                  int Ho, int Wo) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= Wo) return;
+    const ResizeTap tx = resize_tap(x, W, inv), ty = resize_tap(y, H, inv);
+    const double means[3] = {102.9801, 115.9465, 122.7717};        // cfg.PIXEL_MEANS (config.py:170), BGR
+    const uint8_t* r0 = img + (size_t)ty.i0 * W * 3;
+    const uint8_t* r1 = img + (size_t)ty.i1 * W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int cs = rgb ? 2 - c : c;                            // demo.py:106-107: rgb -> bgr
+        const float p00 = (float)((double)r0[tx.i0 * 3 + cs] - means[c]), p01 = (float)((double)r0[tx.i1 * 3 + cs] - means[c]);
+        const float p10 = (float)((double)r1[tx.i0 * 3 + cs] - means[c]), p11 = (float)((double)r1[tx.i1 * 3 + cs] - means[c]);
+        const float h0 = __fadd_rn(__fmul_rn(p00, tx.w0), __fmul_rn(p01, tx.w1));
+        const float h1 = __fadd_rn(__fmul_rn(p10, tx.w0), __fmul_rn(p11, tx.w1));
+        out[((size_t)c * Ho + y) * Wo + x] = __fadd_rn(__fmul_rn(h0, ty.w0), __fmul_rn(h1, ty.w1));
+    }
+}
+
 }  // namespace
+
+extern "C" int sb_prep_image_size(int H, int W, double scale, int* Ho, int* Wo) {
+    if (!Ho || !Wo || H < 1 || W < 1 || !(scale > 0)) return SB_EINVAL;
+    *Ho = (int)rint((double)H * scale);        // cv::saturate_cast<int>(ssize * inv_scale): round half to even
+    *Wo = (int)rint((double)W * scale);
+    return SB_OK;
+}
+
+extern "C" int sb_prep_image(const uint8_t* img, int H, int W, double scale, int rgb_input, float* out,
+                             sb_stream_t stream) {
+    int Ho = 0, Wo = 0;
+    if (!img || !out || sb_prep_image_size(H, W, scale, &Ho, &Wo) != SB_OK || Ho < 1 || Wo < 1) return SB_EINVAL;
+    prep_image_kernel<<<dim3(sb_div_up(Wo, 256), Ho), 256, 0, sb_cs(stream)>>>(img, H, W, 1.0 / scale, rgb_input, out, Ho, Wo);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
 
 extern "C" int sb_fill(float* p, size_t n, float v, sb_stream_t stream) {
     if (n == 0) return SB_OK;
@@ -435,7 +500,26 @@ extern "C" int sb_test_decode(const float* rois_left, const float* rois_right, c
     test_decode_kernel<<<sb_div_up(R, 128), 128, 0, sb_cs(stream)>>>(rois_left, rois_right, bbox_pred, dim_orien,
                                                                      kpts_prob, left_prob, right_prob, im_info, R,
                                                                      n_classes, grid, pred_boxes_left,
-                                                                     pred_boxes_right, dim_orien_out, pred_kpts);
+                                                                     pred_boxes_right, dim_orien_out, pred_kpts,
+                                                                     nullptr, nullptr, 0);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_test_decode_record(const float* rois_left, const float* rois_right, const float* cls_prob,
+                                     const float* bbox_pred, const float* dim_orien, const float* kpts_prob,
+                                     const float* left_prob, const float* right_prob, const float* im_info, int R,
+                                     int n_classes, int grid, float* pred_boxes_left, float* pred_boxes_right,
+                                     float* dim_orien_out, float* pred_kpts, float* record, int record_ld,
+                                     sb_stream_t stream) {
+    if (R == 0) return SB_OK;
+    if (!cls_prob || !record || record_ld < 15 * n_classes + 5) return SB_EINVAL;
+    test_decode_kernel<<<sb_div_up(R, 128), 128, 0, sb_cs(stream)>>>(rois_left, rois_right, bbox_pred, dim_orien,
+                                                                     kpts_prob, left_prob, right_prob, im_info, R,
+                                                                     n_classes, grid, pred_boxes_left,
+                                                                     pred_boxes_right, dim_orien_out, pred_kpts,
+                                                                     cls_prob, record, record_ld);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -89,7 +89,13 @@ __global__ void select_scan_kernel(int* __restrict__ hist, int pass, SelState* _
         if (lane >= o) incl += v;
     }
     const int excl = incl - sum;
-    const int remaining = st->remaining;
+    // lane 0 reads the state once and broadcasts it: the owning lane rewrites st->remaining / st->prefix below, and
+    // under independent thread scheduling a late reader must not see the updated values
+    int remaining = 0;
+    unsigned prefix0 = 0;
+    if (lane == 0) { remaining = st->remaining; prefix0 = st->prefix; }
+    remaining = __shfl_sync(0xffffffffu, remaining, 0);
+    prefix0 = __shfl_sync(0xffffffffu, prefix0, 0);
     const bool mine = excl < remaining && remaining <= incl;
     if (mine) {
         int acc = excl;
@@ -100,7 +106,7 @@ __global__ void select_scan_kernel(int* __restrict__ hist, int pass, SelState* _
             acc += h;
         }
         const int nbits = pass == 2 ? 10 : 11;
-        st->prefix = pass == 0 ? (unsigned)bin : ((st->prefix << nbits) | (unsigned)bin);
+        st->prefix = pass == 0 ? (unsigned)bin : ((prefix0 << nbits) | (unsigned)bin);
         st->remaining = remaining - acc;
         if (pass == 2) { st->n_gt = 0; }
     }

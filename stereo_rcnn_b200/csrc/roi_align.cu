@@ -230,7 +230,9 @@ extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* h
     }
     size_t smem = (size_t)2 * (pooled + 1) * C * sizeof(float);
     if (smem > 200 * 1024) return SB_EINVAL;
-    static size_t cur_max = 48 * 1024;
+    static size_t cur_max_dev[kSbMaxDevices] = {0};
+    size_t& cur_max = cur_max_dev[sb_cur_device()];
+    if (cur_max == 0) cur_max = 48 * 1024;
     if (smem > cur_max) {
         cudaFuncSetAttribute(roi_align_pyramid_nhwc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cur_max = smem;

@@ -74,8 +74,19 @@ _SIGS = {
                              c_void_p, c_void_p]),
     "sb_box_tail": (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p]),
     "sb_test_decode": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int] + [c_void_p] * 4 + [c_void_p]),
+    "sb_test_decode_record": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int] + [c_void_p] * 5 + [c_int, c_void_p]),
     "sb_class_nms": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "sb_prep_image_size": (c_int, [c_int, c_int, c_double, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "sb_prep_image": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p]),
     "sb_fill": (c_int, [c_void_p, c_size_t, c_float, c_void_p]),
+    "sb_peer_mailbox_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sb_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "sb_peer_free": (c_int, [c_void_p]),
+    "sb_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "sb_ipc_import": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "sb_ipc_close": (c_int, [c_void_p]),
+    "sb_peer_put_record": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sb_peer_wait_records": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

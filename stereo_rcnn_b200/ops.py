@@ -3,7 +3,9 @@
 Every function launches hand-written sm_100a kernels from libstereo_b200.so on
 torch's current stream; nothing here computes on the host and nothing falls back.
 """
+import contextlib
 import ctypes
+import threading
 
 import numpy as np
 import torch
@@ -20,17 +22,49 @@ CFG = dict(
     POOLING_SIZE=7, KPTS_GRID=28,
 )
 
-_ws_cache = {}
+class WorkspaceOwner(object):
+    """Scratch buffers of ONE in-flight unit of work (a pipeline slot, a CUDA graph, a test).
+
+    Kernel workspaces hold live state between the launches of one call sequence (select histograms, NMS masks,
+    partial costs), so two sequences that may overlap on the device -- e.g. two CUDA graphs replayed on different
+    streams -- must not share them: each owns a WorkspaceOwner and issues its launches inside
+    ``with ops.workspace_owner(owner):``.  Buffers are grow-only and a replaced buffer is RETIRED, never freed: a
+    CUDA graph captured earlier has its address baked in."""
+
+    def __init__(self):
+        self.bufs, self.retired = {}, []
+
+    def get(self, nbytes, device, tag):
+        key = (str(device), tag)
+        w = self.bufs.get(key)
+        if w is None or w.numel() < nbytes:
+            if w is not None:
+                self.retired.append(w)
+            w = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            self.bufs[key] = w
+        return w
+
+
+_default_owner = WorkspaceOwner()
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def workspace_owner(owner):
+    """route every ops.workspace() request of the enclosed launches to `owner`'s private buffers"""
+    prev = getattr(_tls, "owner", None)
+    _tls.owner = owner
+    try:
+        yield owner
+    finally:
+        _tls.owner = prev
 
 
 def workspace(nbytes, device, tag="default"):
-    """grow-only byte workspace per (device, tag); avoids cudaMalloc in steady state"""
-    key = (str(device), tag)
-    w = _ws_cache.get(key)
-    if w is None or w.numel() < nbytes:
-        w = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
-        _ws_cache[key] = w
-    return w
+    """grow-only byte workspace per (owner, device, tag); avoids cudaMalloc in steady state.  Without an enclosing
+    workspace_owner() the process-wide default owner is used: fine for strictly stream-ordered callers only."""
+    owner = getattr(_tls, "owner", None) or _default_owner
+    return owner.get(nbytes, device, tag)
 
 
 def _f32c(t):
@@ -330,15 +364,52 @@ def test_decode(rois_left, rois_right, bbox_pred, dim_orien, kpts_prob, left_pro
     return pbl, pbr, do, pk
 
 
-def class_nms(scores, boxes_left, cls, score_thresh=0.05, nms_thresh=0.3):
+def test_decode_record(rois_left, rois_right, cls_prob, bbox_pred, dim_orien, kpts_prob, left_prob, right_prob,
+                       im_info, n_classes=2, grid=28, record=None):
+    """test_decode + the [R, 15nc+5] detection record of the image (what ranks all-gather), one launch"""
+    L = _l.load()
+    R = rois_left.shape[0]
+    dev = rois_left.device
+    pbl = torch.empty(R, 4 * n_classes, dtype=torch.float32, device=dev)
+    pbr = torch.empty(R, 4 * n_classes, dtype=torch.float32, device=dev)
+    do = torch.empty(R, 5 * n_classes, dtype=torch.float32, device=dev)
+    pk = torch.empty(R, 5, dtype=torch.float32, device=dev)
+    if record is None:
+        record = torch.empty(R, 15 * n_classes + 5, dtype=torch.float32, device=dev)
+    check(L.sb_test_decode_record(ptr(_f32c(rois_left)), ptr(_f32c(rois_right)), ptr(_f32c(cls_prob)),
+                                  ptr(_f32c(bbox_pred)), ptr(_f32c(dim_orien)), ptr(_f32c(kpts_prob)),
+                                  ptr(_f32c(left_prob)), ptr(_f32c(right_prob)), ptr(_f32c(im_info)), R, n_classes,
+                                  grid, ptr(pbl), ptr(pbr), ptr(do), ptr(pk), ptr(record), record.shape[-1],
+                                  stream_ptr()), "sb_test_decode_record")
+    return pbl, pbr, do, pk, record
+
+
+def class_nms(scores, boxes_left, cls, score_thresh=0.05, nms_thresh=0.3, keep=None, num=None):
     """test_net.py:233-259 on device -> (keep [R] int32 RoI indices in kept order, num [1] int32)"""
     L = _l.load()
     R, nc = scores.shape
-    keep = torch.empty(R, dtype=torch.int32, device=scores.device)
-    num = torch.empty(1, dtype=torch.int32, device=scores.device)
+    if keep is None:
+        keep = torch.empty(R, dtype=torch.int32, device=scores.device)
+    if num is None:
+        num = torch.empty(1, dtype=torch.int32, device=scores.device)
     check(L.sb_class_nms(ptr(_f32c(scores)), ptr(_f32c(boxes_left)), R, nc, int(cls), float(score_thresh),
                          float(nms_thresh), ptr(keep), ptr(num), stream_ptr()), "sb_class_nms")
     return keep, num
+
+
+def prep_image(img_u8, scale, rgb_input=False, out=None):
+    """prep_im_for_blob (blob.py:44-64) on the device: uint8 [H,W,3] -> fp32 [3,Ho,Wo] (BGR - means, resized)"""
+    L = _l.load()
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and img_u8.shape[2] == 3
+    H, W = img_u8.shape[:2]
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    check(L.sb_prep_image_size(H, W, float(scale), ctypes.byref(ho), ctypes.byref(wo)), "sb_prep_image_size")
+    if out is None:
+        out = torch.empty(3, ho.value, wo.value, dtype=torch.float32, device=img_u8.device)
+    assert tuple(out.shape) == (3, ho.value, wo.value)
+    check(L.sb_prep_image(ptr(img_u8.contiguous()), H, W, float(scale), 1 if rgb_input else 0, ptr(out), stream_ptr()),
+          "sb_prep_image")
+    return out
 
 
 def l2_flush(buf):

@@ -39,3 +39,111 @@ def max_over_ranks(value_ms, device, world, dist=None):
     t = torch.tensor([float(value_ms)], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+class RecordGather(object):
+    """The exchange step: `gather(slot, rec [R, C]) -> [world, R, C]`, one call per step and in-flight slot.
+
+    mode "peer" (default on CUDA): the ranks store their record straight into each other's mailboxes over
+        NVLink and release a sequence flag (csrc/peer.cu; CUDA IPC handles travel once through torch.distributed).
+        No NCCL kernel, no shared communicator stream: slots do not serialise on each other.
+    mode "nccl": one `all_gather_into_tensor` per step on a process group PRIVATE to the slot (a communicator used
+        from several streams would serialise the slots on ProcessGroupNCCL's internal stream).
+    On CPU tensors (gloo host tests) the collective is always torch.distributed's.
+    world == 1: identity.  `describe()` says which path is live; a peer set-up failure is reported there, not hidden.
+    """
+
+    def __init__(self, world, rank, device, dist=None, n_slots=1, mode=None, rec_shape=(REC_ROIS, REC_COLS),
+                 timeout_s=20.0):
+        import os
+        self.world, self.rank, self.dist, self.n_slots = world, rank, dist, n_slots
+        self.device = torch.device(device)
+        self.rec_shape = tuple(rec_shape)
+        self.rec_floats = (int(rec_shape[0] * rec_shape[1]) + 3) // 4 * 4
+        self.timeout_s = timeout_s
+        mode = mode or os.environ.get("SB_GATHER", "peer")
+        self.mode = "none" if world == 1 else ("nccl" if self.device.type != "cuda" else mode)
+        self.note = ""
+        self.out = [torch.empty((world,) + self.rec_shape, dtype=torch.float32, device=self.device)
+                    for _ in range(n_slots)] if world > 1 else None
+        if self.mode == "peer":
+            try:
+                self._setup_peer()
+            except Exception as e:      # reported in describe() and in the bench line
+                self.note = "peer set-up failed (%s: %s), using nccl" % (type(e).__name__, e)
+                self.mode = "nccl"
+            # every rank must take the same path
+            ok = torch.tensor([1 if self.mode == "peer" else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok[0]) == 0 and self.mode == "peer":
+                self.mode, self.note = "nccl", "a peer rank could not map the mailboxes, using nccl"
+        if self.mode == "nccl":
+            self.groups = [dist.new_group() if self.device.type == "cuda" else None for _ in range(n_slots)]
+
+    # ---- peer path ----
+    def _setup_peer(self):
+        import ctypes
+        from . import lib
+        L = lib.load()
+        nb = L.sb_peer_mailbox_bytes(self.n_slots, self.world, self.rec_floats)
+        if nb == 0:
+            raise ValueError("unsupported mailbox geometry")
+        own = ctypes.c_void_p()
+        lib.check(L.sb_peer_alloc(nb, ctypes.byref(own)), "sb_peer_alloc")
+        h = (ctypes.c_ubyte * 64)()
+        lib.check(L.sb_ipc_export(own, h), "sb_ipc_export")
+        mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
+        allh = torch.empty(self.world, 64, dtype=torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(allh.view(-1), mine)
+        allh = allh.cpu()
+        self._boxes = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                self._boxes[r] = own.value
+            else:
+                hb = (ctypes.c_ubyte * 64)(*allh[r].tolist())
+                p = ctypes.c_void_p()
+                lib.check(L.sb_ipc_import(hb, ctypes.byref(p)), "sb_ipc_import(rank %d)" % r)
+                self._boxes[r] = p.value
+        self._own = own
+        self._err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._staged = [torch.zeros(self.rec_floats, dtype=torch.float32, device=self.device)
+                        for _ in range(self.n_slots)]
+        self.dist.barrier()
+
+    def check(self):
+        """host-side: raise if a wait timed out (reads one device int; call outside timed regions)"""
+        if self.mode == "peer":
+            e = int(self._err[0])
+            if e:
+                raise RuntimeError("record gather: rank %d never delivered" % (e - 1))
+
+    def __call__(self, slot, rec):
+        if self.world == 1:
+            return rec.unsqueeze(0)
+        out = self.out[slot]
+        if self.mode == "peer":
+            from . import lib
+            L = lib.load()
+            n = rec.numel()
+            src = rec
+            if n != self.rec_floats or not rec.is_contiguous() or rec.data_ptr() % 16:
+                src = self._staged[slot]
+                src[:n].copy_(rec.reshape(-1))
+            st = lib.stream_ptr()
+            lib.check(L.sb_peer_put_record(lib.ptr(src), self._boxes, self.n_slots, self.world, self.rec_floats,
+                                           self.rank, slot, st), "sb_peer_put_record")
+            lib.check(L.sb_peer_wait_records(self._own, self.n_slots, self.world, self.rec_floats, slot,
+                                             lib.ptr(out), lib.ptr(self._err), float(self.timeout_s), st),
+                      "sb_peer_wait_records")
+            return out
+        self.dist.all_gather_into_tensor(out.view((-1,) + self.rec_shape[1:]), rec.contiguous(),
+                                         group=self.groups[slot])
+        return out
+
+    def describe(self):
+        if self.world == 1:
+            return "none (1 GPU)"
+        d = {"peer": "own kernels over NVLink peer memory (CUDA IPC mailboxes, posted 128-bit stores + release flags)",
+             "nccl": "ncclAllGather (torch.distributed.all_gather_into_tensor), one communicator per in-flight slot"}[self.mode]
+        return d + ("; " + self.note if self.note else "")

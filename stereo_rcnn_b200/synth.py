@@ -167,3 +167,34 @@ _GAINS = (("RCNN_layer0.0", 1.0 / 64), ("RCNN_toplayer", 0.0625), ("RCNN_latlaye
           ("RCNN_rpn.RPN_cls_score", 2.0), ("kpts_class", 0.1))
 
 
+
+
+def make_reference_init_state_dict(seed=3, n_classes=2):
+    """The reference's OWN random initialisation, restated with seeded per-key RNG streams: ResNet convs
+    N(0, sqrt(2 / (kh*kw*Cout))) and BatchNorm weight 1 / bias 0 / mean 0 / var 1 (lib/model/stereo_rcnn/resnet.py:123-129);
+    FPN / RPN / predictor layers N(0, 0.01) (bbox_pred, dim_orien_pred 0.001; kpts_class 0.1) with zero bias, RCNN_top and
+    RCNN_kpts N(0, 0.02) with zero bias (stereo_rcnn.py:47-85).  Un-normalised: activations grow to ~1e6 by C4, far
+    outside fp16 -- the tf32 precision mode is the one that runs such weights."""
+    import torch
+    sd = OrderedDict()
+    for k, shp in param_shapes(n_classes).items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode()) + 77) % (2 ** 31))
+        leaf = k.rsplit(".", 1)[1]
+        is_bn = ".bn" in k or "downsample.1" in k or k.startswith("RCNN_layer0.1")
+        if is_bn:
+            t = torch.ones(shp) if leaf in ("weight", "running_var") else torch.zeros(shp)
+        elif leaf == "bias":
+            t = torch.zeros(shp)
+        elif k.startswith("RCNN_layer"):
+            t = torch.randn(shp, generator=g) * (2.0 / (shp[2] * shp[3] * shp[0])) ** 0.5
+        else:
+            std = 0.01
+            if k.startswith(("RCNN_bbox_pred", "RCNN_dim_orien_pred")):
+                std = 0.001
+            elif k.startswith("kpts_class"):
+                std = 0.1
+            elif k.startswith(("RCNN_top", "RCNN_kpts")):
+                std = 0.02
+            t = torch.randn(shp, generator=g) * std
+        sd[k] = t.float().contiguous()
+    return sd

@@ -22,7 +22,51 @@ from stereo_rcnn_b200.synth import synth_pair, gen_rois  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def demo_goldens():
+    """(8) input pipeline and (9) the reference forward on a crop of the reference's own demo pair.
+
+    demo/left.png|right.png (375x1242) are read where they lie; only small uint8 crops are stored.  The blob is made
+    by the reference's own recipe (demo.py:106-120 / blob.py:44-64: BGR - PIXEL_MEANS, cv2.resize fx=fy=scale,
+    INTER_LINEAR) with the cv2 of this image, then fed to the reference's `_StereoRCNN.forward` with our seeded weights."""
+    import cv2
+    ref = ref_shim.load()
+    cfg = ref.cfg
+    left = cv2.imread(os.path.join(ref_shim.REF, "demo/left.png"))        # BGR uint8 (= imread(...)[:,:,::-1])
+    right = cv2.imread(os.path.join(ref_shim.REF, "demo/right.png"))
+    assert left.shape == (375, 1242, 3)
+
+    def blob(im, scale):
+        f = im.astype(np.float32, copy=True)
+        f -= cfg.PIXEL_MEANS
+        f = cv2.resize(f, None, None, fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)
+        return np.ascontiguousarray(f.transpose(2, 0, 1))
+    # (8) prep_im_for_blob on a 64x96 crop at the demo scale 1.6 and at a KITTI-like non-dyadic scale
+    c8 = left[170:234, 560:656].copy()
+    np.savez_compressed(os.path.join(HERE, "prep_image.npz"), crop_bgr=c8, scale_a=1.6, blob_a=blob(c8, 1.6),
+                        scale_b=600.0 / 370.0, blob_b=blob(c8, 600.0 / 370.0), cv2_version=cv2.__version__)
+    # (9) forward on a 192x320 crop of the demo pair (cars + road), scale 1.6 -> 307x512
+    y0, x0 = 150, 480
+    cl, cr = left[y0:y0 + 192, x0:x0 + 320].copy(), right[y0:y0 + 192, x0:x0 + 320].copy()
+    scale = 1.6
+    bl, br = blob(cl, scale), blob(cr, scale)
+    sd = model.make_state_dict(3)
+    m = ref_shim.build_reference_model(sd)
+    info = torch.tensor([[float(bl.shape[1]), float(bl.shape[2]), scale]])
+    d = torch.zeros(1)
+    with torch.no_grad():
+        outs = m(torch.from_numpy(bl)[None], torch.from_numpy(br)[None], info, d, d, d, d, d, d)
+    names = ["rois_left", "rois_right", "cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob",
+             "left_border_prob", "right_border_prob"]
+    gold = {n: o.numpy() for n, o in zip(names, outs[:8])}
+    np.savez_compressed(os.path.join(HERE, "forward_demo.npz"), crop_left_bgr=cl, crop_right_bgr=cr, scale=scale,
+                        crop_origin=np.array([y0, x0]), weight_seed=3, blob_checksum=np.array([bl.sum(dtype=np.float64),
+                        br.sum(dtype=np.float64)]), **gold)
+    print("demo goldens written")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "demo":
+        return demo_goldens()
     ref = ref_shim.load()
     cfg = ref.cfg
     calib = ref_shim.demo_calib()
@@ -152,6 +196,7 @@ def main():
                         scores=ns["scores"].numpy(), pred_boxes_left=ns["pred_boxes_left"].numpy(), cls=1,
                         score_thresh=0.05, nms_thresh=float(cfg.TEST.NMS), kept_rois=kept_rois,
                         cls_dets_left=ns2["cls_dets_left"].numpy(), cls_kpts=ns2["cls_kpts"].numpy())
+    demo_goldens()
     print("goldens written to", HERE)
 
 

@@ -304,8 +304,6 @@ def test_forward_small_fp16_operand_path(golden_dir, monkeypatch):
     test_forward_small_vs_oracle_and_reference_golden(golden_dir)
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: the tf32 forward last ran green "
-                   "before the epilogue rewrite (its conv-level tests are green on the final build)")
 def test_forward_small_tf32_path(golden_dir, monkeypatch):
     """the kind::tf32 mode (fp32 storage, pre-biased residual stream) meets the same bars"""
     monkeypatch.setenv("SB_PRECISION", "tf32")
@@ -361,7 +359,6 @@ def test_latency_and_throughput_schedules_agree():
         assert rel_err(a[k].cpu(), b[k].cpu()) < 1e-5, k
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent; not yet executed on hardware")
 @pytest.mark.parametrize("half", [False, True])
 def test_conv_tc_store_modes_are_exact_transforms(half):
     """out_mode 1 (store rounded to TF32) and 2 (store +0x1000 in the bit pattern), and res_biased (residual stored

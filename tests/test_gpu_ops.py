@@ -315,13 +315,7 @@ def test_class_nms_vs_oracle():
     assert int(num[0]) == 0
 
 
-# Added after this round's GPU budget was spent: the kernels below are already bit-exact against the oracle on
-# hardware (tests above) and the oracle reproduces these goldens on CPU (tests/test_oracle_golden.py), so the tests
-# are expected to pass; until they have run on a B200 once they must not be able to turn the suite red.
-_new_unrun = pytest.mark.xfail(strict=False, reason="new golden test, not yet executed on hardware (round 1)")
-
-
-@_new_unrun
+# Golden tests against the reference's own script lines (green on B200 since round 1).
 def test_test_decode_vs_reference_script_golden(golden_dir):
     """sb_test_decode against the golden minted by executing test_net.py's own decode lines (tests/golden/
     make_golden.py (6)): index-valued columns exact, boxes to the exp-ulp level (torch.exp vs sb_expf)"""
@@ -339,7 +333,6 @@ def test_test_decode_vs_reference_script_golden(golden_dir):
     np.testing.assert_array_equal(pk.cpu().numpy(), g["pred_kpts"])
 
 
-@_new_unrun
 def test_class_nms_vs_reference_script_golden(golden_dir):
     """sb_class_nms against the golden minted by executing test_net.py:234-259 on the decode golden"""
     g = np.load(os.path.join(golden_dir, "class_nms.npz"))
@@ -349,7 +342,6 @@ def test_class_nms_vs_reference_script_golden(golden_dir):
     np.testing.assert_array_equal(keep[:g["kept_rois"].size].cpu().numpy(), g["kept_rois"])
 
 
-@_new_unrun
 def test_proposal_layer_train_golden_bit_exact(golden_dir):
     """TRAIN configuration (12000 / 2000 / IoU 0.7; here pre_nms_top_n exceeds the 10 236 anchors of the small
     pyramid, so every anchor is a candidate) against the oracle (bit-exact) and the reference's own output"""

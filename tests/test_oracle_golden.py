@@ -221,3 +221,32 @@ def test_per_class_nms_matches_reference_script_lines(golden_dir):
     np.testing.assert_array_equal(np.asarray(keep, np.int64), g["kept_rois"])
     j = int(g["cls"])
     np.testing.assert_array_equal(g["pred_boxes_left"][keep][:, 4 * j:4 * j + 4], g["cls_dets_left"][:, :4])
+
+
+def test_prep_image_matches_cv2_golden(golden_dir):
+    """8f-3: the restated prep_im_for_blob (blob.py:44-64) against blobs made by the reference's recipe with the
+    cv2 of the build image (make_golden.py (8)), at the demo scale and at a non-dyadic KITTI scale"""
+    g = _load(golden_dir, "prep_image.npz")
+    for tag in ("a", "b"):
+        got = ops.prep_image(g["crop_bgr"], float(g["scale_" + tag]))
+        assert got.shape == g["blob_" + tag].shape
+        np.testing.assert_allclose(got, g["blob_" + tag], rtol=0, atol=6.2e-5)      # <= 2 ulp at |x| <= 256
+
+
+@pytest.mark.slow
+def test_forward_on_reference_demo_crop_matches_reference(golden_dir):
+    """the oracle on a 192x320 crop of the reference's demo/left.png|right.png (blob by the reference's recipe)
+    against the reference's own forward on the same crop"""
+    g = _load(golden_dir, "forward_demo.npz")
+    sc = float(g["scale"])
+    bl, br = ops.prep_image(g["crop_left_bgr"], sc), ops.prep_image(g["crop_right_bgr"], sc)
+    np.testing.assert_allclose([bl.sum(dtype=np.float64), br.sum(dtype=np.float64)], g["blob_checksum"], rtol=1e-6)
+    sd = model.make_state_dict(int(g["weight_seed"]))
+    info = torch.tensor([[float(bl.shape[1]), float(bl.shape[2]), sc]])
+    o = model.forward(sd, torch.from_numpy(bl)[None], torch.from_numpy(br)[None], info)
+    same = (np.abs(o["rois_left"].numpy() - g["rois_left"]) < 1e-2).all(2) & \
+           (np.abs(o["rois_right"].numpy() - g["rois_right"]) < 1e-2).all(2)
+    assert same.mean() > 0.97, same.mean()          # the blobs differ by <= 2 ulp: a rare proposal may swap
+    if same.all():
+        for n in ("cls_prob", "bbox_pred", "dim_orien_pred", "kpts_prob", "left_border_prob", "right_border_prob"):
+            np.testing.assert_allclose(o[n].numpy().reshape(g[n].shape), g[n], rtol=1e-3, atol=1e-4, err_msg=n)
