@@ -32,149 +32,13 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int kRowBytes = 128;  // one swizzle row per pixel per K-step: 32 fp32 (kind::tf32, K=8 per MMA)
-                                // or 64 fp16 (kind::f16, K=16 per MMA); four MMAs per K-step either way
 constexpr int TW = 16, TH = 8;  // spatial patch of a 3x3 tile (TW*TH == BLOCK_M)
 // epilogue warps per CTA: 8 (one big CTA per SM) or 4 ("small" variant: two CTAs per SM for layers with few tiles)
 constexpr int kMaxCout = 2048;   // scale/shift staged in shared memory
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 8 rows * 128 B
-// | version=1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=TF32 (2<<7),
-// B=TF32 (2<<10), A/B K-major (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {
-    return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
-        " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
-    return v;
-}
-// bring `bytes` (multiple of 16, 16-byte aligned) of global memory into L2 ahead of use; no registers, no smem
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred P;\n"
-        "elect.sync _|P, 0xffffffff;\n"
-        "selp.b32 %0, 1, 0, P;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
 
 // ------------------------------------------------------------------ kernel
 constexpr size_t epi_smem(int ew) { return (size_t)ew * (32 * 8 * 16); }
@@ -660,6 +524,264 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ flat (1x1) kernel with a TMA epilogue
+// The 1x1 convolutions of the bottlenecks -- conv1, conv3 (+ residual), the downsample branch -- the stem GEMM, the
+// box-head FCs and the RPN head are plain [M, Cin] x [Cin, Cout] GEMMs with dense [M, Cout] outputs and only 1-32
+// K-steps per tile: their time is the epilogue.  This kernel keeps the producer / MMA-issuer warps of the generic
+// kernel above and replaces the epilogue by one in which global memory is touched by TMA only:
+//   * each epilogue warp owns a 32-row x 32-column box of the tile per step ("chunk"); the accumulator chunk comes
+//     out of TMEM with one tcgen05.ld (one row per thread), which is already the layout of a 128-byte-swizzled TMA
+//     box: row r of the box is 128 contiguous bytes, its 16-byte groups XOR-permuted by (r & 7) -- conflict-free for
+//     the row-per-thread 128-bit accesses, no transposition through shared memory;
+//   * the residual box arrives by TMA load into a warp-private ring (three boxes: one being consumed, two in
+//     flight -- issued two chunks ahead, across tile boundaries, before the accumulator is complete), the result
+//     overwrites it in place and leaves by TMA store; the fp16 twin leaves through a 64-byte-swizzled half box;
+//   * no address arithmetic, predicates or global LD/ST in the warps: M and Cout tails are clipped / zero-filled
+//     by the tensor maps.  Buffer reuse is ordered by cp.async.bulk.wait_group.read, not by barriers between warps.
+struct FlatParams {
+    const float* scale;
+    const float* shift;
+    const float* residual;    // for the L2 bulk prefetch two tiles ahead (the data path goes through map_res)
+    long long M;
+    int Cout, res_ld;
+    int num_m_tiles, num_n_tiles, num_k_blocks;
+    int relu, has16, pdl_late;
+    unsigned long long* trace;
+};
+
+constexpr int flat_epi_warp_bytes(bool res, bool f32) { return f32 ? ((res ? 3 : 2) * 4096 + 4096) : 4096; }
+
+template <int BLOCK_N, int kStages, bool HAS_RES, bool F32>
+__global__ void __launch_bounds__(320, 1)
+conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_o32,
+                    const __grid_constant__ CUtensorMap map_o16, const FlatParams p) {
+    static_assert(!HAS_RES || F32, "the residual epilogue produces the fp32 stream");
+    constexpr uint32_t kABytes = BLOCK_M * kRowBytes, kBBytes = BLOCK_N * kRowBytes;
+    constexpr int BLOCK_K = 64;
+    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256 : 512;
+    constexpr int NB = HAS_RES ? 3 : 2;                                  // fp32 boxes per warp
+    constexpr int kEpiWarpBytes = flat_epi_warp_bytes(HAS_RES, F32);
+    constexpr int kF16Off = F32 ? NB * 4096 : 0;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi = smem + kStages * kStageBytes;                          // 1024-aligned (stage bytes are multiples of 4096)
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi + 8 * kEpiWarpBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* rfull = tempty + 2;                                         // [8 warps][3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 24);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * kTraceWords : nullptr;
+    if (tr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = gtimer(); tr[8] = clock64(); tr[6] = smid;
+    }
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        if (HAS_RES) prefetch_tmap(&map_res);
+        if (F32) prefetch_tmap(&map_o32);
+        if (p.has16) prefetch_tmap(&map_o16);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+            for (int i = 0; i < 24; ++i) mbar_init(&rfull[i], 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (!p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tr && threadIdx.x == 0) { tr[1] = gtimer(); tr[9] = clock64(); }
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    mbar_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(&map_a, &full[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
+                    tma_load_2d(&map_b, &full[stage], sa + kABytes, kb * BLOCK_K, nt * BLOCK_N);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc(BLOCK_N, true);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (tr && lane == 0 && kb == 0 && tile == (int)blockIdx.x) { tr[2] = gtimer(); tr[10] = clock64(); }
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (kb == p.num_k_blocks - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (tr && lane == 0) { tr[3] = gtimer(); tr[11] = clock64(); }
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int q = warp & 3;            // TMEM lane quarter this warp may touch
+        const int ew = warp - 2;
+        const int half = ew >> 2;
+        constexpr int kColsPerWarp = BLOCK_N / 2 >= 32 ? BLOCK_N / 2 : 32;
+        constexpr int kChunks = kColsPerWarp / 32;
+        const int col_begin = half * kColsPerWarp;
+        const bool has_cols = col_begin < BLOCK_N;
+        uint8_t* ebase = epi + ew * kEpiWarpBytes;
+        uint64_t* my_rfull = rfull + ew * 3;
+        const bool has16 = p.has16 != 0;
+        const bool relu = p.relu != 0;
+        uint32_t g = 0;                    // running chunk number of this warp (ring position)
+        // coordinates of chunk gi in this warp's chunk sequence (tiles of this CTA x chunks of the warp)
+        auto issue_res = [&](uint32_t gi) {
+            const uint32_t ts = gi / kChunks, k = gi - ts * kChunks;
+            const long long tile = (long long)blockIdx.x + (long long)ts * gridDim.x;
+            if (tile >= num_tiles) return;
+            const int mt = (int)(tile / p.num_n_tiles), nt = (int)(tile - (long long)mt * p.num_n_tiles);
+            const uint32_t b = gi % NB;
+            mbar_expect_tx(&my_rfull[b], 4096);
+            tma_load_2d(&map_res, &my_rfull[b], ebase + b * 4096, nt * BLOCK_N + col_begin + 32 * (int)k, mt * BLOCK_M + q * 32);
+        };
+        // residual rows two tiles ahead go to L2 with a bulk prefetch (layers 1-2: the residual stream lives in HBM)
+        auto prefetch_res_tile = [&](int t) {
+            if (t >= num_tiles) return;
+            const int pmt = t / p.num_n_tiles, pnt = t - pmt * p.num_n_tiles;
+            const long long m = (long long)pmt * BLOCK_M + q * 32 + lane;
+            const int c0 = pnt * BLOCK_N + col_begin;
+            if (m < p.M && c0 < p.Cout)
+                prefetch_l2_bulk(p.residual + m * p.res_ld + c0, (uint32_t)min(kColsPerWarp, p.Cout - c0) * 4u);
+        };
+        if (HAS_RES && has_cols) {
+            if (lane == 0) { issue_res(0); issue_res(1); }
+            prefetch_res_tile(blockIdx.x + gridDim.x);
+        }
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+            if (HAS_RES && has_cols) prefetch_res_tile(tile + 2 * gridDim.x);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            if (has_cols) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col_begin);
+                const int m0 = mt * BLOCK_M + q * 32;
+#pragma unroll
+                for (int k = 0; k < kChunks; ++k) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + 32 * k, v);
+                    const int c0 = nt * BLOCK_N + col_begin + 32 * k;
+                    const uint32_t b = F32 ? g % NB : 0;
+                    uint8_t* box32 = ebase + b * 4096;
+                    uint8_t* box16 = ebase + kF16Off + (g & 1) * 2048;
+                    const uint32_t row32 = smem_u32(box32) + lane * 128;
+                    const uint32_t row16 = smem_u32(box16) + lane * 64;
+                    if (HAS_RES) mbar_wait(&my_rfull[b], (g / NB) & 1);       // this chunk's residual box has landed
+                    tmem_ld_wait();
+                    if (k == kChunks - 1) {      // the accumulator stage is drained: the MMA warp may reuse it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    uint32_t hprev0 = 0, hprev1 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int cj = c0 + 4 * j;
+                        const bool ok = cj < p.Cout;
+                        const float4 sc = (p.scale && ok) ? __ldg(reinterpret_cast<const float4*>(p.scale + cj)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        const float4 sh = (p.shift && ok) ? __ldg(reinterpret_cast<const float4*>(p.shift + cj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 x;
+                        x.x = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+                        x.y = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+                        x.z = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+                        x.w = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+                        const uint32_t a32 = row32 + ((uint32_t)(j ^ (lane & 7)) << 4);
+                        if (HAS_RES) {
+                            const float4 r = lds128(a32);
+                            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                        }
+                        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                        if (F32) sts128(a32, x);
+                        if (has16) {
+                            __half2 lo = __floats2half2_rn(x.x, x.y), hi = __floats2half2_rn(x.z, x.w);
+                            const uint32_t h0 = *reinterpret_cast<uint32_t*>(&lo), h1 = *reinterpret_cast<uint32_t*>(&hi);
+                            if (j & 1) sts128u(row16 + ((uint32_t)((j >> 1) ^ ((lane >> 1) & 3)) << 4), make_uint4(hprev0, hprev1, h0, h1));
+                            else { hprev0 = h0; hprev1 = h1; }
+                        }
+                    }
+                    fence_proxy_async();          // the boxes were written through the generic proxy; TMA reads them
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (F32) tma_store_2d(&map_o32, box32, c0, m0);
+                        if (has16) tma_store_2d(&map_o16, box16, c0, m0);
+                        tma_commit_group();
+                        // everything but this chunk's stores has left shared memory: the box of chunk g-1 is free
+                        tma_wait_group_read<1>();
+                        if (HAS_RES) issue_res(g + 2);
+                    }
+                    __syncwarp();
+                    ++g;
+                }
+            } else {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            if (tr && warp == 2 && lane == 0 && tile == (int)blockIdx.x) { tr[4] = gtimer(); tr[12] = clock64(); }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_wait_group_read<0>();      // shared memory must outlive the last stores' reads
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tr && threadIdx.x == 0) { tr[5] = gtimer(); tr[13] = clock64(); }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -679,12 +801,12 @@ EncodeTiledFn get_encode() {
 }
 
 bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, bool f16) {
+              const cuuint32_t* box, bool f16, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -756,6 +878,53 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     }
     if (up) return launch_t<BN, ST, false, true, false, EW>(ma, mb, p, st);
     return res ? launch_t<BN, ST, true, false, false, EW>(ma, mb, p, st) : launch_t<BN, ST, false, false, false, EW>(ma, mb, p, st);
+}
+
+
+template <int BN, int ST, bool RES, bool F32>
+int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo32,
+                const CUtensorMap& mo16, const FlatParams& p, int max_ctas, cudaStream_t st) {
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 8 * (size_t)flat_epi_warp_bytes(RES, F32) +
+                            (2 * ST + 4 + 24) * 8 + 16 + 1024;
+    static_assert(smem <= 227 * 1024, "smem budget");
+    static bool attr_done[kSbMaxDevices] = {false};
+    bool& attr = attr_done[sb_cur_device()];
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_flat_kernel<BN, ST, RES, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    int slots = sb_num_sms();
+    if (max_ctas > 0 && max_ctas < slots) slots = max_ctas;
+    const int grid = tiles < slots ? tiles : slots;
+    static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_flat_kernel<BN, ST, RES, F32>, ma, mb, mr, mo32, mo16, p);
+    SB_LAUNCHED();
+    if (le != cudaSuccess) return (int)le;
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+// can this conv run through the flat kernel with the TMA epilogue?  (fp16 operands, 1x1, dense [M, Cout] rows)
+bool flat_eligible(const sb_conv_desc* d, bool patch) {
+    static const bool on = getenv("SB_TC_FLAT") == nullptr || atoi(getenv("SB_TC_FLAT")) != 0;
+    if (!on || d->in_dtype != 1 || patch || d->up_src || d->out_mode != 0) return false;
+    if (d->out_h_stride != (long long)d->Wo * d->out_w_stride || d->out_n_stride != (long long)d->Ho * d->out_h_stride) return false;
+    if (d->residual && !d->out) return false;
+    if (d->out && (((reinterpret_cast<uintptr_t>(d->out) + 4ull * d->out_coff) & 15) || (d->out_w_stride & 3))) return false;
+    if (d->out16 && (((reinterpret_cast<uintptr_t>(d->out16) + 2ull * d->out_coff) & 15) || (d->out_w_stride & 7))) return false;
+    return true;
 }
 
 }  // namespace
@@ -844,13 +1013,20 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     }
     if (small) BN = 128;
     if (const char* e = getenv("SB_TC_BLOCK_N")) { int v = atoi(e); if ((v == 128 || v == 256) && d->Cout >= 256 && !small) BN = v; }
+    // flat kernel with the TMA epilogue: instances exist for these (tile width, outputs) combinations
+    bool flat = !small && flat_eligible(d, p.patch != 0);
+    if (flat) {
+        if (d->out && BN == 256) BN = 128;            // fp32 boxes of a 256-wide tile do not fit beside the stages
+        const bool f16only = !d->out;
+        flat = (BN == 32 && d->out && !d->out16 && !d->residual) || (BN == 64 && f16only) || BN == 128 || (BN == 256 && f16only);
+    }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
     if (g_trace && g_trace_n < g_trace_cap) {
         const int id = g_trace_n++;
         p.trace = g_trace + (size_t)id * kTraceCtas * kTraceWords;
         int* v = g_trace_info[id].v;
         v[0] = d->Cin; v[1] = d->Cout; v[2] = d->kh; v[3] = (int)p.M; v[4] = BN; v[5] = p.num_m_tiles * p.num_n_tiles;
-        v[6] = p.num_k_blocks; v[7] = d->residual ? 1 : 0; v[8] = d->up_src ? 1 : 0; v[9] = small ? 1 : 0;
+        v[6] = p.num_k_blocks; v[7] = d->residual ? 1 : 0; v[8] = d->up_src ? 1 : 0; v[9] = small ? 1 : (flat ? 2 : 0);
         v[10] = d->max_ctas; v[11] = d->N;
     }
     CUtensorMap ma, mb;
@@ -874,6 +1050,37 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         if (!make_map(&mb, d->wgt, 2, dims, strides, box, f16)) return SB_EINVAL;
     }
     cudaStream_t st = sb_cs(stream);
+    if (flat) {
+        FlatParams fp;
+        fp.scale = d->scale; fp.shift = d->shift; fp.residual = d->residual;
+        fp.M = p.M; fp.Cout = d->Cout; fp.res_ld = d->res_ld;
+        fp.num_m_tiles = p.num_m_tiles; fp.num_n_tiles = p.num_n_tiles; fp.num_k_blocks = p.num_k_blocks;
+        fp.relu = d->relu; fp.has16 = d->out16 ? 1 : 0; fp.pdl_late = p.pdl_late; fp.trace = p.trace;
+        CUtensorMap mr = ma, mo32 = ma, mo16 = ma;      // unused maps still need a valid descriptor
+        const cuuint64_t dims[2] = {(cuuint64_t)d->Cout, (cuuint64_t)p.M};
+        const cuuint32_t box[2] = {32, 32};
+        if (d->residual) {
+            const cuuint64_t str[1] = {(cuuint64_t)d->res_ld * 4};
+            if (!make_map(&mr, d->residual, 2, dims, str, box, false)) return SB_EINVAL;
+        }
+        if (d->out) {
+            const cuuint64_t str[1] = {(cuuint64_t)d->out_w_stride * 4};
+            if (!make_map(&mo32, d->out + d->out_coff, 2, dims, str, box, false)) return SB_EINVAL;
+        }
+        if (d->out16) {
+            const cuuint64_t str[1] = {(cuuint64_t)d->out_w_stride * 2};
+            if (!make_map(&mo16, reinterpret_cast<const __half*>(d->out16) + d->out_coff, 2, dims, str, box, true,
+                          CU_TENSOR_MAP_SWIZZLE_64B))
+                return SB_EINVAL;
+        }
+        const int mc = d->max_ctas;
+        if (BN == 32) return launch_flat<32, 6, false, true>(ma, mb, mr, mo32, mo16, fp, mc, st);
+        if (BN == 64) return launch_flat<64, 8, false, false>(ma, mb, mr, mo32, mo16, fp, mc, st);
+        if (BN == 256) return launch_flat<256, 4, false, false>(ma, mb, mr, mo32, mo16, fp, mc, st);
+        if (d->residual) return launch_flat<128, 3, true, true>(ma, mb, mr, mo32, mo16, fp, mc, st);
+        if (d->out) return launch_flat<128, 4, false, true>(ma, mb, mr, mo32, mo16, fp, mc, st);
+        return launch_flat<128, 6, false, false>(ma, mb, mr, mo32, mo16, fp, mc, st);
+    }
     if (small) return launch<128, 2, 4>(ma, mb, p, st);
     // epilogue-bound shapes (at most 8 K-steps per tile: the 1x1 convs of the bottlenecks, the deconv quarters)
     // can run with 16 epilogue warps: SB_TC_EW16 = 0 never (default), 1 by this rule, 2 whenever the tile is wide

@@ -234,23 +234,31 @@ compact_kernel(const float* __restrict__ prob, int A, const SelState* __restrict
 
 // Rank sort of the K unique 64-bit keys (descending): rank(i) = #{j : key_j > key_i}.  K^2 = 36 M
 // compare-adds spread over ceil(K/64) CTAs replace the 91 barrier-separated steps of a single-CTA bitonic
-// sort (13 us instead of 105 us at K = 6000); keys are streamed through shared memory as broadcast reads.
-__global__ void __launch_bounds__(64)
+// sort; keys are streamed through shared memory as broadcast reads.  Four threads share one key, each
+// counting a quarter of every tile (the per-thread compare chain was the launch's whole latency: 54 us at
+// K = 6000 with one thread per key), and their counts meet in shared memory.
+__global__ void __launch_bounds__(256)
 rank_sort_kernel(const unsigned long long* __restrict__ cand, int K, int* __restrict__ order,
                  float* __restrict__ score) {
-    __shared__ unsigned long long tile[1024];
-    const int i = blockIdx.x * 64 + threadIdx.x;
+    __shared__ unsigned long long tile[2048];
+    __shared__ int part[4][64];
+    const int kk = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + kk;
     const unsigned long long my = i < K ? cand[i] : ~0ULL;
     int rank = 0;
-    for (int base = 0; base < K; base += 1024) {
-        const int cnt = min(1024, K - base);
-        for (int j = threadIdx.x; j < cnt; j += 64) tile[j] = cand[base + j];
+    for (int base = 0; base < K; base += 2048) {
+        const int cnt = min(2048, K - base);
+        for (int j = threadIdx.x; j < 2048; j += 256) tile[j] = j < cnt ? cand[base + j] : 0ULL;   // 0 never outranks
         __syncthreads();
-#pragma unroll 8
-        for (int j = 0; j < cnt; ++j) rank += tile[j] > my;
+        const int j0 = q * 512;
+#pragma unroll 16
+        for (int j = 0; j < 512; ++j) rank += tile[j0 + j] > my;
         __syncthreads();
     }
-    if (i < K) {
+    part[q][kk] = rank;
+    __syncthreads();
+    if (q == 0 && i < K) {
+        rank = part[0][kk] + part[1][kk] + part[2][kk] + part[3][kk];
         order[rank] = (int)(0xFFFFFFFFu - (unsigned)(my & 0xFFFFFFFFu));
         score[rank] = key_to_float((unsigned)(my >> 32));
     }
@@ -418,7 +426,7 @@ extern "C" int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_l
         count_eq_kernel<<<nblocks, 256, 0, st>>>(prob, A, state, block_eq, block_gt); SB_LAUNCHED();
         block_scan_kernel<<<1, 1024, 0, st>>>(block_eq, block_gt, nblocks, state); SB_LAUNCHED();
         compact_kernel<<<nblocks, 256, 0, st>>>(prob, A, state, block_eq, block_gt, cand, K); SB_LAUNCHED();
-        rank_sort_kernel<<<(K + 63) / 64, 64, 0, st>>>(cand, K, order, score); SB_LAUNCHED();
+        rank_sort_kernel<<<(K + 63) / 64, 256, 0, st>>>(cand, K, order, score); SB_LAUNCHED();
         decode_kernel<<<(K + 255) / 256, 256, 0, st>>>(order, K, deltas, im_info + 3 * b, ac, prop_l, prop_r);
         SB_LAUNCHED();
         SB_CHECK_LAUNCH();

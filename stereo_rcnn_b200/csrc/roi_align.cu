@@ -130,59 +130,87 @@ __device__ __forceinline__ int roi_level(const float* roi) {
     return (int)l - 2;
 }
 
-// one CTA per (roi, output row ph); C % 4 == 0; dynamic smem = 2 * (P+1) * C floats
+// One CTA per (roi, block of RB output rows); C % 4 == 0.  The CTA walks the RB+1 lattice rows of its block with a
+// rolling pair of rows in shared memory (each lattice row is built once per CTA instead of once per output row: at
+// RB = 7 the 14x14 pooling does 8/7 instead of 2x the tap work), and the tap geometry -- fp64 weights, offsets -- is
+// built once per (row, column) by the first threads instead of once per channel vector.
+// dynamic smem = 2 * (P+1) * C floats for the lattice rows + (RB+1) * (P+1) tap records.
+struct TapRec {
+    double w00, w01, w10, w11;
+    long long off;      // element offset of the top-left source pixel, or -1 for a zero tap
+};
+
 __global__ void __launch_bounds__(256)
-roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int P,
+roi_align_pyramid_nhwc(PyramidArgs a, int C, const float* __restrict__ rois, int P, int RB,
                        float* __restrict__ out, int out_ld, int out_coff, int round_tf32) {
-    extern __shared__ float4 lat[];  // [2][P+1][C/4]
-    const int n = blockIdx.x, ph = blockIdx.y;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = P + 1;
+    const int C4 = C >> 2;
+    float4* lat = reinterpret_cast<float4*>(smem_raw);                               // [2][L][C4]
+    TapRec* taps = reinterpret_cast<TapRec*>(smem_raw + (size_t)2 * L * C4 * sizeof(float4));   // [RB+1][L]
+    const int n = blockIdx.x, ph0 = blockIdx.y * RB;
+    const int rows = min(RB, P - ph0);                 // output rows of this CTA
     const float* roi = rois + 5 * n;
     const int lv = roi_level(roi);
     const int H = a.H[lv], W = a.W[lv];
     const float* __restrict__ feat = a.feat[lv];
-    const int L = P + 1;
     const RoiGeom g = roi_geom(roi, a.scale[lv], L, L);
-    const int C4 = C >> 2;
-    for (int e = threadIdx.x; e < 2 * L * C4; e += blockDim.x) {
-        const int c4 = e % C4, tp = e / C4;
-        const int row = tp / L, pw = tp % L;
-        const Tap t = make_tap(g, ph + row, pw, H, W);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!t.zero) {
-            const float4* f00 = reinterpret_cast<const float4*>(feat + (((size_t)g.batch * H + t.h0) * W + t.w0) * C) + c4;
-            const float4 p00 = __ldg(f00), p01 = __ldg(f00 + C4);
-            const float4 p10 = __ldg(f00 + (size_t)W * C4), p11 = __ldg(f00 + (size_t)W * C4 + C4);
-            v.x = tap_value(t, p00.x, p01.x, p10.x, p11.x);
-            v.y = tap_value(t, p00.y, p01.y, p10.y, p11.y);
-            v.z = tap_value(t, p00.z, p01.z, p10.z, p11.z);
-            v.w = tap_value(t, p00.w, p01.w, p10.w, p11.w);
-        }
-        lat[e] = v;
+    for (int e = threadIdx.x; e < (rows + 1) * L; e += blockDim.x) {
+        const int r = e / L, pw = e - r * L;
+        const Tap t = make_tap(g, ph0 + r, pw, H, W);
+        TapRec tr;
+        tr.w00 = t.w00; tr.w01 = t.w01; tr.w10 = t.w10; tr.w11 = t.w11;
+        tr.off = t.zero ? -1 : (long long)((((size_t)g.batch * H + t.h0) * W + t.w0) * C);
+        taps[e] = tr;
     }
     __syncthreads();
-    float* orow = out + ((size_t)n * P + ph) * P * out_ld + out_coff;
-    for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
-        const int c4 = e % C4, pw = e / C4;
-        const float4 a0 = lat[(0 * L + pw) * C4 + c4], a1 = lat[(0 * L + pw + 1) * C4 + c4];
-        const float4 b0 = lat[(1 * L + pw) * C4 + c4], b1 = lat[(1 * L + pw + 1) * C4 + c4];
-        float4 o;  // avg_pool2d(2, stride 1): ((a+b)+(c+d)) * 0.25
-        o.x = __fmul_rn(__fadd_rn(__fadd_rn(a0.x, a1.x), __fadd_rn(b0.x, b1.x)), 0.25f);
-        o.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, a1.y), __fadd_rn(b0.y, b1.y)), 0.25f);
-        o.z = __fmul_rn(__fadd_rn(__fadd_rn(a0.z, a1.z), __fadd_rn(b0.z, b1.z)), 0.25f);
-        o.w = __fmul_rn(__fadd_rn(__fadd_rn(a0.w, a1.w), __fadd_rn(b0.w, b1.w)), 0.25f);
-        if (round_tf32 == 2) {      // fp16 output for the kind::f16 convs (same element strides, half the bytes)
-            __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            __half* ob = reinterpret_cast<__half*>(out) + ((size_t)n * P + ph) * P * out_ld + out_coff;
-            *reinterpret_cast<uint2*>(ob + (size_t)pw * out_ld + 4 * c4) = pk;
-            continue;
+    const size_t wstep = (size_t)W * C4;
+    for (int r = 0; r <= rows; ++r) {
+        float4* cur = lat + (size_t)(r & 1) * L * C4;
+        for (int e = threadIdx.x; e < L * C4; e += blockDim.x) {
+            const int c4 = e % C4, pw = e / C4;
+            const TapRec& t = taps[r * L + pw];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.off >= 0) {
+                const float4* f00 = reinterpret_cast<const float4*>(feat + t.off) + c4;
+                const float4 p00 = __ldg(f00), p01 = __ldg(f00 + C4);
+                const float4 p10 = __ldg(f00 + wstep), p11 = __ldg(f00 + wstep + C4);
+                v.x = (float)((double)p00.x * t.w00 + (double)p01.x * t.w01 + (double)p10.x * t.w10 + (double)p11.x * t.w11);
+                v.y = (float)((double)p00.y * t.w00 + (double)p01.y * t.w01 + (double)p10.y * t.w10 + (double)p11.y * t.w11);
+                v.z = (float)((double)p00.z * t.w00 + (double)p01.z * t.w01 + (double)p10.z * t.w10 + (double)p11.z * t.w11);
+                v.w = (float)((double)p00.w * t.w00 + (double)p01.w * t.w01 + (double)p10.w * t.w10 + (double)p11.w * t.w11);
+            }
+            cur[e] = v;
         }
-        if (round_tf32) {   // the pooled tile is read only by tensor-core convs: make TF32 truncation exact
-            o.x = sb_round_tf32(o.x); o.y = sb_round_tf32(o.y); o.z = sb_round_tf32(o.z); o.w = sb_round_tf32(o.w);
+        __syncthreads();
+        if (r == 0) continue;
+        const float4* top = lat + (size_t)((r - 1) & 1) * L * C4;
+        const int ph = ph0 + r - 1;
+        float* orow = out + ((size_t)n * P + ph) * P * out_ld + out_coff;
+        for (int e = threadIdx.x; e < P * C4; e += blockDim.x) {
+            const int c4 = e % C4, pw = e / C4;
+            const float4 a0 = top[pw * C4 + c4], a1 = top[(pw + 1) * C4 + c4];
+            const float4 b0 = cur[pw * C4 + c4], b1 = cur[(pw + 1) * C4 + c4];
+            float4 o;  // avg_pool2d(2, stride 1): ((a+b)+(c+d)) * 0.25
+            o.x = __fmul_rn(__fadd_rn(__fadd_rn(a0.x, a1.x), __fadd_rn(b0.x, b1.x)), 0.25f);
+            o.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, a1.y), __fadd_rn(b0.y, b1.y)), 0.25f);
+            o.z = __fmul_rn(__fadd_rn(__fadd_rn(a0.z, a1.z), __fadd_rn(b0.z, b1.z)), 0.25f);
+            o.w = __fmul_rn(__fadd_rn(__fadd_rn(a0.w, a1.w), __fadd_rn(b0.w, b1.w)), 0.25f);
+            if (round_tf32 == 2) {      // fp16 output for the kind::f16 convs (same element strides, half the bytes)
+                __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                __half* ob = reinterpret_cast<__half*>(out) + ((size_t)n * P + ph) * P * out_ld + out_coff;
+                *reinterpret_cast<uint2*>(ob + (size_t)pw * out_ld + 4 * c4) = pk;
+                continue;
+            }
+            if (round_tf32) {   // the pooled tile is read only by tensor-core convs: make TF32 truncation exact
+                o.x = sb_round_tf32(o.x); o.y = sb_round_tf32(o.y); o.z = sb_round_tf32(o.z); o.w = sb_round_tf32(o.w);
+            }
+            *reinterpret_cast<float4*>(orow + (size_t)pw * out_ld + 4 * c4) = o;
         }
-        *reinterpret_cast<float4*>(orow + (size_t)pw * out_ld + 4 * c4) = o;
+        __syncthreads();       // the next lattice row overwrites `top`
     }
 }
 
@@ -228,7 +256,9 @@ extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* h
         // stereo_rcnn.py:128: scale = feat.size(2) / im_info[0][0] (python float), then float(...)
         a.scale[l] = (float)((double)heights[l] / (double)im_h);
     }
-    size_t smem = (size_t)2 * (pooled + 1) * C * sizeof(float);
+    // output rows per CTA: all of a 7x7 tile (8 lattice rows for 7 outputs), half of a 14x14 tile
+    const int RB = pooled <= 8 ? pooled : (pooled + 1) / 2;
+    size_t smem = (size_t)2 * (pooled + 1) * C * sizeof(float) + (size_t)(RB + 1) * (pooled + 1) * sizeof(TapRec);
     if (smem > 200 * 1024) return SB_EINVAL;
     static size_t cur_max_dev[kSbMaxDevices] = {0};
     size_t& cur_max = cur_max_dev[sb_cur_device()];
@@ -237,8 +267,8 @@ extern "C" int sb_roi_align_pyramid_nhwc(const float* const* feats, const int* h
         cudaFuncSetAttribute(roi_align_pyramid_nhwc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cur_max = smem;
     }
-    dim3 grid(R, pooled);
-    roi_align_pyramid_nhwc<<<grid, 256, smem, sb_cs(stream)>>>(a, C, rois, pooled, out, out_ld, out_coff, round_tf32);
+    dim3 grid(R, (pooled + RB - 1) / RB);
+    roi_align_pyramid_nhwc<<<grid, 256, smem, sb_cs(stream)>>>(a, C, rois, pooled, RB, out, out_ld, out_coff, round_tf32);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;
