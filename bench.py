@@ -80,10 +80,12 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------
-def make_inputs(rank):
+def make_inputs(rank, j=0):
+    """pair j of rank `rank` (seeded; j > 0 only with --microbatch)"""
     from stereo_rcnn_b200.synth import DEMO_P2, DEMO_P3, gen_rois, synth_pair
-    left, right = synth_pair(H_NET, W_NET, seed=3 + rank, shift=48)
-    b, k, p = gen_rois(D_ALIGN, seed=3 + rank)
+    seed = 3 + rank + 1000 * j
+    left, right = synth_pair(H_NET, W_NET, seed=seed, shift=48)
+    b, k, p = gen_rois(D_ALIGN, seed=seed)
     return left, right, (b, k, p), (DEMO_P2, DEMO_P3)
 
 
@@ -105,12 +107,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     from stereo_rcnn_b200 import ops, parallel, pipeline
     from stereo_rcnn_b200.synth import make_state_dict
-    left, right, (b, k, p), (P2, P3) = make_inputs(rank)
+    MB = max(1, args.microbatch)          # pairs per step of one in-flight slot (batched through every launch)
+    pairs = [make_inputs(rank, j) for j in range(MB)]
+    P2, P3 = pairs[0][3]
     calib4 = ops.calib_vec(P2, P3)
-    host_l = torch.from_numpy(left)[None].pin_memory()
-    host_r = torch.from_numpy(right)[None].pin_memory()
+    host_l = torch.from_numpy(np.stack([q[0] for q in pairs])).pin_memory()      # [MB,3,H,W]
+    host_r = torch.from_numpy(np.stack([q[1] for q in pairs])).pin_memory()
     iml, imr = host_l.to(dev), host_r.to(dev)
-    rois3d = tuple(torch.from_numpy(x).to(dev) for x in (b, k, p))
+    rois3d = [tuple(torch.from_numpy(x).to(dev) for x in q[2]) for q in pairs]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
     n_inflight = max(1, args.inflight)
     use_graph = os.environ.get("SB_GRAPH", "1") != "0"
@@ -120,20 +124,22 @@ def run_ours(args):
     # the public end-to-end API of the package (stereo_rcnn_b200.pipeline): StereoPipeline.step is the call a user
     # makes, GraphSlot is one in-flight step (own stream, fixed inputs, private workspaces, CUDA graph)
     pipe_lat = pipeline.StereoPipeline(sd, dev, scale=SCALE)             # one pair at a time: lowest latency
-    pipe = pipeline.StereoPipeline(sd, dev, throughput=True, scale=SCALE) if n_inflight > 1 else pipe_lat
+    pipe = pipeline.StereoPipeline(sd, dev, throughput=True, scale=SCALE) if (n_inflight > 1 or MB > 1) else pipe_lat
     copy_stream = torch.cuda.Stream(device=dev)
-    gather = parallel.RecordGather(world, rank, dev, dist, n_slots=n_inflight + 1, mode=args.gather)
+    gather = parallel.RecordGather(world, rank, dev, dist, n_slots=n_inflight + 1, mode=args.gather,
+                                   rec_shape=(MB * N_ROIS, REC_COLS))
 
     class Slot(pipeline.GraphSlot):
-        """a GraphSlot plus the bench's host side: the pinned-host staging pair for the next H2D and the host
-        landing buffers of the slot's results"""
+        """a GraphSlot plus the bench's host side: the pinned-host staging of the next H2D and the host landing
+        buffers of the slot's results.  `mb` pairs per step (batched through every launch)."""
 
-        def __init__(self, pipe, own_stream, index):
-            super().__init__(pipe, iml, imr, calib4, rois3d, own_stream=own_stream, use_graph=use_graph)
-            self.index = index
-            self.host_rec = torch.empty(world, N_ROIS, REC_COLS).pin_memory()
-            self.host_dis = torch.empty(D_ALIGN).pin_memory()
-            self.staging = [(torch.empty_like(iml), torch.empty_like(imr)) for _ in range(1 if own_stream else 2)]
+        def __init__(self, pipe, own_stream, index, gather, mb):
+            self.mb, self.gather, self.index = mb, gather, index
+            self.h_l, self.h_r = host_l[:mb], host_r[:mb]
+            super().__init__(pipe, iml[:mb], imr[:mb], calib4, rois3d[:mb], own_stream=own_stream, use_graph=use_graph)
+            self.host_rec = torch.empty(world, mb * N_ROIS, REC_COLS).pin_memory()
+            self.host_dis = torch.empty(mb, D_ALIGN).pin_memory()
+            self.staging = [(torch.empty_like(self.iml), torch.empty_like(self.imr)) for _ in range(1 if own_stream else 2)]
             self.ready = [torch.cuda.Event() for _ in self.staging]
             self.freed = [torch.cuda.Event() for _ in self.staging]
             for ev in self.freed:
@@ -143,17 +149,17 @@ def run_ours(args):
         def prefetch(self, j):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(self.freed[j])
-                self.staging[j][0].copy_(host_l, non_blocking=True)
-                self.staging[j][1].copy_(host_r, non_blocking=True)
+                self.staging[j][0].copy_(self.h_l, non_blocking=True)
+                self.staging[j][1].copy_(self.h_r, non_blocking=True)
                 self.ready[j].record(copy_stream)
 
         def step_resident(self):
             rec, keep, nkeep, st, dis = self.run()
-            return gather(self.index, rec[0]), dis[0]
+            return self.gather(self.index, rec.view(-1, REC_COLS)), dis
 
         def step_e2e(self):
-            """H2D of this slot's next pair (pinned host -> staging, copy stream) overlaps compute; every step still
-            moves its own 28.6 MB in and its records out inside the timed region"""
+            """H2D of this slot's next pair(s) (pinned host -> staging, copy stream) overlaps compute; every step
+            still moves its own 28.6 MB per pair in and its records out inside the timed region"""
             if use_graph:
                 nst = len(self.staging)
                 j = self.k % nst
@@ -167,15 +173,19 @@ def run_ours(args):
                 self.prefetch((self.k + 1) % nst)         # the next pair's H2D runs under this compute
                 self.k += 1
             else:
-                self.load(host_l, host_r)
+                self.load(self.h_l, self.h_r)
             rec, keep, nkeep, st, dis = self.run()
-            g = gather(self.index, rec[0])
+            g = self.gather(self.index, rec.view(-1, REC_COLS))
             self.host_rec.copy_(g, non_blocking=True)
-            self.host_dis.copy_(dis[0], non_blocking=True)
-            return g, dis[0]
+            for j in range(self.mb):
+                self.host_dis[j].copy_(dis[j], non_blocking=True)
+            return g, dis
 
-    lat_slot = Slot(pipe_lat, False, n_inflight if n_inflight > 1 else 0)
-    slots = [Slot(pipe, True, i) for i in range(n_inflight)] if n_inflight > 1 else [lat_slot]
+    # the latency slot always runs ONE pair at a time (batch 1, the reference's test configuration)
+    gather_lat = gather if MB == 1 else parallel.RecordGather(world, rank, dev, dist, n_slots=1, mode=args.gather)
+    pipelined = n_inflight > 1 or MB > 1
+    lat_slot = Slot(pipe_lat, False, n_inflight if (pipelined and MB == 1) else 0, gather_lat, 1)
+    slots = [Slot(pipe, True, i, gather, MB) for i in range(n_inflight)] if pipelined else [lat_slot]
     host_rec, host_dis = slots[0].host_rec, slots[0].host_dis
 
     def timed(fn, steps, warmup):
@@ -234,11 +244,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.launch_count()
-    pipe.step(iml, imr, calib4, rois3d)                 # one eager step only to count our kernel launches
+    pipe.step(iml, imr, calib4, rois3d)                 # one eager step (MB pairs) only to count our kernel launches
     launches = ops.launch_count() - l0
     W = max(args.warmup, 3)
     single = None
-    if n_inflight == 1:
+    if not pipelined:
         total_ms = timed(slots[0].step_resident, args.steps, W)
         e2e_ms = timed(slots[0].step_e2e, args.steps, 1)
     else:
@@ -252,20 +262,25 @@ def run_ours(args):
     # the exchange step alone (records already packed): device time of one gather per step, max over ranks
     gather_ms = None
     if world > 1:
-        rec0 = slots[0].outputs[0][0]
+        rec0 = slots[0].outputs[0].view(-1, REC_COLS)
         gather_ms = timed(lambda: gather(slots[0].index, rec0), args.steps, W) / args.steps
+        gather.check()
     # every in-flight slot must have produced the result of the one-pair-at-a-time run on the same input: the
     # schedules differ only in tile widths / stream forks, proposals are index-exact and records agree to rounding
     torch.cuda.synchronize()
-    ref_rec = lat_slot.outputs[0][0]
     checks = []
     for sl in slots:
-        r_ = sl.outputs[0][0]
-        checks.append(float((r_ - ref_rec).abs().max() / ref_rec.abs().max()))
+        for j in range(sl.mb):
+            if j == 0:
+                ref_rec = lat_slot.outputs[0][0]
+            else:       # pair j alone through the batch-1 pipeline
+                ref_rec = pipe_lat.step(iml[j:j + 1], imr[j:j + 1], calib4, rois3d[j:j + 1])[0][0]
+                torch.cuda.synchronize()
+            checks.append(float((sl.outputs[0][j] - ref_rec).abs().max() / ref_rec.abs().max()))
     sampler.stop_flag = True
     ms_per_step = total_ms / args.steps
-    value = world * args.steps / (total_ms / 1e3)
-    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    value = world * args.steps * MB / (total_ms / 1e3)
+    e2e_value = world * args.steps * MB / (e2e_ms / 1e3)
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live with CUDA events ----
     roof = None
@@ -273,7 +288,7 @@ def run_ours(args):
     parity = None
     if rank == 0:
         pk = peaks()
-        conv_ms, conv_classes = conv_time_per_step(pipe, iml, imr)
+        conv_ms, conv_classes = conv_time_per_step(pipe, iml[:1], imr[:1])
         tflops = 2 * TC_GMACS_PER_PAIR * 1e9 / (conv_ms / 1e3) / 1e12
         half = pipe.eng.half
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::%s implicit GEMM, all conv/FC launches of one step)" % ("f16" if half else "tf32"),
@@ -289,7 +304,7 @@ def run_ours(args):
                 "conv_ms_serialized": round(conv_ms, 3),
                 # each class issued alone back to back; compare tflops with `peak` and algorithmic_tb_per_s with hbm_peak
                 "by_class": conv_classes, "hbm_peak_tb_per_s": round(pk["hbm_gbs"] / 1e3, 3),
-                "achieved_in_step_lower_bound": round(2 * TC_GMACS_PER_PAIR * 1e9 / (ms_per_step / 1e3) / 1e12, 2)}
+                "achieved_in_step_lower_bound": round(2 * TC_GMACS_PER_PAIR * MB * 1e9 / (ms_per_step / 1e3) / 1e12, 2)}
         if world == 1 and not args.no_cpu_baseline:
             cpu_base, parity = cpu_baseline_sample(pipe_lat)
     if world > 1:
@@ -305,17 +320,18 @@ def run_ours(args):
         "config": {"workload": "configs[1]: batch-1 inference per GPU, synthetic KITTI-shape pair 2x[1,3,600,1987], "
                                "full pipeline incl. dense_align (D=%d synthetic poses)" % D_ALIGN,
                    "weights": "seeded variance-preserving random init (stereo_rcnn_b200.synth.make_state_dict(3))",
-                   "l2": ("256 MB flush between timed iterations" if n_inflight == 1 else
+                   "l2": ("256 MB flush between timed iterations" if not pipelined else
                           "inputs larger than L2: every step reads ~0.4 GB of weights and streams ~5.9 GB of activations "
                           "through the 126 MB L2; steps of the %d in-flight pairs overlap, so no flush between them "
                           "(single_stream: flushed)" % n_inflight),
-                   "inflight": n_inflight, "schedule": "throughput: %d independent batch-1 pairs in flight, one stream + CUDA "
-                   "graph + private workspaces each, no intra-pair forks" % n_inflight if n_inflight > 1 else "latency (one pair in flight)",
+                   "inflight": n_inflight, "microbatch": MB, "pairs_per_step": MB, "schedule": ("throughput: %d independent steps in flight (%d pair(s) per step, batched "
+                   "through every launch), one stream + CUDA graph + private workspaces each, no intra-pair forks" % (n_inflight, MB))
+                   if pipelined else "latency (one pair in flight)",
                    "api": "stereo_rcnn_b200.pipeline.StereoPipeline.step via pipeline.GraphSlot",
                    "cuda_graph": use_graph, "parallelism": "dp%d (1 pair/rank)" % world,
                    "gather": gather.describe()},
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s",
-                "h2d_bytes_per_step": int(host_l.numel() * 4 * 2),
+                "h2d_bytes_per_step": int(slots[0].h_l.numel() * 4 * 2),
                 "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},
         "gpu_launches": int(launches) * args.steps,
         "inflight_vs_single_max_rel_diff": [round(c, 9) for c in checks],
@@ -542,6 +558,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default=None, choices=[None, "peer", "nccl"],
                     help="record exchange at N>1: own peer-memory kernels (default) or ncclAllGather")
+    ap.add_argument("--microbatch", type=int, default=int(os.environ.get("SB_MICROBATCH", "1")),
+                    help="pairs per step of one in-flight slot, batched through every launch (M-batching)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("SB_INFLIGHT", "3")),
                     help="independent pairs in flight per GPU (each batch-1, own stream + CUDA graph)")
     args = ap.parse_args()

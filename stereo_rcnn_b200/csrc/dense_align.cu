@@ -5,17 +5,23 @@
 // loop over RoIs with ~150 tiny kernels and host scalar reads each, builds a 38 MB uv grid,
 // then ~10 full passes over [50 x D x P x 3] intermediates per stage (3.7 GB each at D=2048).
 //
-// Here:
-//   K1 upsample2x_kernel : both images, F.upsample(x2, bilinear, align_corners=True) written
-//      once as pixel-interleaved float4 (c0,c1,c2,0) so that a bilinear tap is one 128-bit load.
-//   K2/K3 dense_stage_kernel<0|1>: grid (RoI, lattice slice).  Thread 0 builds the 3D box (corners, the
-//      three visible planes by the nearest-vertex rule); every thread owns lattice pixels (row-major,
-//      strided), runs the ray/plane/in-box test, samples the left image once and accumulates the SAD of all
-//      50 (coarse) or 20 (fine) depth hypotheses in registers; warp-shuffle + smem reduction to one partial
-//      row per CTA.  The fine stage re-derives the coarse argmin from the partial rows (fixed slice order).
-//   K4 dense_final_kernel: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere ->
+// Here (round 2): the 2x-upsampled pair is never materialised (round 1 wrote 2 x 76 MB of it per call).
+//   K1/K2 dense_stage_kernel<0|1>: grid (RoI, row slice).  Thread 0 builds the 3D box (corners, the three visible
+//      planes by the nearest-vertex rule).  The CTA then walks its lattice rows; per row
+//        (a) one thread per lattice pixel runs the ray / plane / in-box test and samples the LEFT image -- each tap
+//            of F.grid_sample is a pixel of the 2x image, recomputed from <= 4 source pixels with the exact
+//            arithmetic of F.upsample(align_corners=True);
+//        (b) the span of RIGHT-image columns that the row's hypotheses can reach is reduced over the row, and the
+//            CTA builds that strip of the 2x image (one or two rows of it) ONCE in shared memory -- SURVEY 8(d)'s
+//            compulsory traffic: R_rows * (W_span + D_span) pixels per RoI instead of 70 * P gathers;
+//        (c) thread (pixel, hypothesis group) evaluates d = fb / (depth + dz), the bilinear taps out of the strip
+//            (taps outside the strip -- never in practice -- are recomputed from the source) and keeps the SAD of its
+//            13 / 25 hypotheses in registers across rows;
+//      then a warp-shuffle + shared-memory reduction to one partial row per CTA.  The fine stage re-derives the
+//      coarse argmin from the partial rows (fixed slice order).
+//   K3 dense_final_kernel: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere ->
 //      return dis_init" early-out.
-// Nothing but the two upsampled images (2 x 76 MB), a few KB of partial sums and D x 2 outputs touches HBM.
+// Only the source pair (28.6 MB, L2-resident), a few KB of partial sums and D x 2 outputs touch HBM.
 //
 // Arithmetic mirrors oracle/csrc/oracle_ops.c (which is pinned to the reference's Python):
 // every fp32 step is an explicit _rn intrinsic in the reference's evaluation order.
@@ -23,40 +29,34 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256)
-upsample2x_kernel(const float* __restrict__ im0, const float* __restrict__ im1, int H, int W,
-                  float4* __restrict__ up0, float4* __restrict__ up1) {
-    const float* __restrict__ src = blockIdx.z ? im1 : im0;
-    float4* __restrict__ dst = blockIdx.z ? up1 : up0;
-    const int OH = 2 * H, OW = 2 * W;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= OW) return;
-    const float rh = (OH > 1) ? __fdiv_rn((float)(H - 1), (float)(OH - 1)) : 0.f;
-    const float rw = (OW > 1) ? __fdiv_rn((float)(W - 1), (float)(OW - 1)) : 0.f;
-    const float sy = __fmul_rn(rh, (float)y);
+// One pixel (y, x) of F.upsample(im, scale 2, bilinear, align_corners=True) of a planar [3,H,W] image, with the
+// arithmetic of the reference's materialised tensor (dense_align.py:255-257): same ratios, same operation order.
+struct UpGeom { float rh, rw; int H, W; };
+__device__ __forceinline__ float4 up_pixel(const float* __restrict__ src, const UpGeom& ug, int y, int x) {
+    const float sy = __fmul_rn(ug.rh, (float)y);
     const int y1 = (int)sy;
-    const int yp = (y1 < H - 1) ? 1 : 0;
+    const int yp = (y1 < ug.H - 1) ? 1 : 0;
     const float ly1 = __fsub_rn(sy, (float)y1), ly0 = __fsub_rn(1.f, ly1);
-    const float sx = __fmul_rn(rw, (float)x);
+    const float sx = __fmul_rn(ug.rw, (float)x);
     const int x1 = (int)sx;
-    const int xp = (x1 < W - 1) ? 1 : 0;
+    const int xp = (x1 < ug.W - 1) ? 1 : 0;
     const float lx1 = __fsub_rn(sx, (float)x1), lx0 = __fsub_rn(1.f, lx1);
     float o[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float* r0 = src + ((size_t)c * H + y1) * W;
-        const float* r1 = r0 + (size_t)yp * W;
-        float top = __fadd_rn(__fmul_rn(lx0, __ldg(r0 + x1)), __fmul_rn(lx1, __ldg(r0 + x1 + xp)));
-        float bot = __fadd_rn(__fmul_rn(lx0, __ldg(r1 + x1)), __fmul_rn(lx1, __ldg(r1 + x1 + xp)));
+        const float* r0 = src + ((size_t)c * ug.H + y1) * ug.W;
+        const float* r1 = r0 + (size_t)yp * ug.W;
+        const float top = __fadd_rn(__fmul_rn(lx0, __ldg(r0 + x1)), __fmul_rn(lx1, __ldg(r0 + x1 + xp)));
+        const float bot = __fadd_rn(__fmul_rn(lx0, __ldg(r1 + x1)), __fmul_rn(lx1, __ldg(r1 + x1 + xp)));
         o[c] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
     }
-    dst[(size_t)y * OW + x] = make_float4(o[0], o[1], o[2], 0.f);
+    return make_float4(o[0], o[1], o[2], 0.f);
 }
 
 struct Consts {
     float s2f, f32, bl32, fb32, cx32, cy32, fw2, fh2;
     int FH, FW;
+    UpGeom ug;
 };
 
 struct RoiCtx {
@@ -157,84 +157,179 @@ __device__ __forceinline__ bool ray_test(const RoiCtx& g, float u, float v, cons
     return m;
 }
 
-// F.grid_sample(bilinear, border, align_corners=True) on the interleaved image
-__device__ __forceinline__ float3 grid_sample(const float4* __restrict__ im, int H, int W, float gx, float gy) {
+// F.grid_sample(bilinear, border, align_corners=True): coordinates and weights of one sample
+struct Samp {
+    int xi0, yi0;
+    bool okx, row1;          // tap columns / rows that exist and carry weight
+    float nw, ne, sw, se;
+};
+__device__ __forceinline__ void samp_x(Samp& s, float gx, int W) {
     float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
-    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
     ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    const float x0 = floorf(ix);
+    const float x1 = __fadd_rn(x0, 1.f);
+    s.ne = __fsub_rn(ix, x0);     // wx1 (scaled by the row weights in samp_weights)
+    s.nw = __fsub_rn(x1, ix);     // wx0
+    s.xi0 = (int)x0;
+    s.okx = s.xi0 + 1 <= W - 1;
+}
+__device__ __forceinline__ void samp_y(Samp& s, float gy, int H, float* wy0, float* wy1) {
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
     iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
-    const float x0 = floorf(ix), y0 = floorf(iy);
-    const float x1 = __fadd_rn(x0, 1.f), y1 = __fadd_rn(y0, 1.f);
-    const float wx1 = __fsub_rn(ix, x0), wx0 = __fsub_rn(x1, ix);
-    const float wy1 = __fsub_rn(iy, y0), wy0 = __fsub_rn(y1, iy);
-    const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0);
-    const float sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
-    const int xi0 = (int)x0, yi0 = (int)y0;
-    const bool okx = xi0 + 1 <= W - 1, oky = yi0 + 1 <= H - 1;
-    const float4* p = im + (size_t)yi0 * W + xi0;
-    const float4 a = __ldg(p);
-    float3 v = make_float3(__fmul_rn(a.x, nw), __fmul_rn(a.y, nw), __fmul_rn(a.z, nw));
-    if (okx) {
-        const float4 b = __ldg(p + 1);
-        v.x = __fadd_rn(v.x, __fmul_rn(b.x, ne)); v.y = __fadd_rn(v.y, __fmul_rn(b.y, ne)); v.z = __fadd_rn(v.z, __fmul_rn(b.z, ne));
-    }
-    if (oky && wy1 != 0.f) {   // a zero-weight row adds +-0 : skipped loads do not change the sum
-        const float4 c = __ldg(p + W);
-        v.x = __fadd_rn(v.x, __fmul_rn(c.x, sw)); v.y = __fadd_rn(v.y, __fmul_rn(c.y, sw)); v.z = __fadd_rn(v.z, __fmul_rn(c.z, sw));
-        if (okx) {
-            const float4 d = __ldg(p + W + 1);
-            v.x = __fadd_rn(v.x, __fmul_rn(d.x, se)); v.y = __fadd_rn(v.y, __fmul_rn(d.y, se)); v.z = __fadd_rn(v.z, __fmul_rn(d.z, se));
-        }
+    const float y0 = floorf(iy);
+    const float y1 = __fadd_rn(y0, 1.f);
+    *wy1 = __fsub_rn(iy, y0);
+    *wy0 = __fsub_rn(y1, iy);
+    s.yi0 = (int)y0;
+    s.row1 = (s.yi0 + 1 <= H - 1) && (*wy1 != 0.f);   // a zero-weight row adds +-0: skipping it does not change the sum
+}
+__device__ __forceinline__ void samp_weights(Samp& s, float wy0, float wy1) {
+    const float wx0 = s.nw, wx1 = s.ne;
+    s.nw = __fmul_rn(wx0, wy0); s.ne = __fmul_rn(wx1, wy0);
+    s.sw = __fmul_rn(wx0, wy1); s.se = __fmul_rn(wx1, wy1);
+}
+// accumulate the (up to) four taps in the reference's order nw, ne, sw, se
+__device__ __forceinline__ float3 samp_combine(const Samp& s, const float4 a, const float4 b, const float4 c, const float4 d) {
+    float3 v = make_float3(__fmul_rn(a.x, s.nw), __fmul_rn(a.y, s.nw), __fmul_rn(a.z, s.nw));
+    if (s.okx) { v.x = __fadd_rn(v.x, __fmul_rn(b.x, s.ne)); v.y = __fadd_rn(v.y, __fmul_rn(b.y, s.ne)); v.z = __fadd_rn(v.z, __fmul_rn(b.z, s.ne)); }
+    if (s.row1) {
+        v.x = __fadd_rn(v.x, __fmul_rn(c.x, s.sw)); v.y = __fadd_rn(v.y, __fmul_rn(c.y, s.sw)); v.z = __fadd_rn(v.z, __fmul_rn(c.z, s.sw));
+        if (s.okx) { v.x = __fadd_rn(v.x, __fmul_rn(d.x, s.se)); v.y = __fadd_rn(v.y, __fmul_rn(d.y, s.se)); v.z = __fadd_rn(v.z, __fmul_rn(d.z, s.se)); }
     }
     return v;
 }
+// a sample straight from the source image (left-image samples; right-image taps that fall outside the strip)
+__device__ __forceinline__ float3 sample_fly(const float* __restrict__ im, const Consts& k, const Samp& s) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = up_pixel(im, k.ug, s.yi0, s.xi0);
+    const float4 b = s.okx ? up_pixel(im, k.ug, s.yi0, s.xi0 + 1) : z4;
+    const float4 c = s.row1 ? up_pixel(im, k.ug, s.yi0 + 1, s.xi0) : z4;
+    const float4 d = (s.row1 && s.okx) ? up_pixel(im, k.ug, s.yi0 + 1, s.xi0 + 1) : z4;
+    return samp_combine(s, a, b, c, d);
+}
 
-// One stage of the depth search for one (RoI, lattice slice).  Every thread owns lattice pixels
-// q = slice*blockDim + tid (+ nslices*blockDim ...), keeps the SAD of all NH hypotheses in registers and the
-// CTA writes one partial row [NH costs, valid-pixel count] to `part`.
-template <int NH>
-__device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, const float4* __restrict__ upL,
-                                            const float4* __restrict__ upR, const float* __restrict__ rdis,
-                                            float* __restrict__ red /*[8][NH+1]*/, int slice, int nslices,
-                                            float* __restrict__ part /*[NH+1] global*/) {
-    float acc[NH];
+constexpr int kStripMax = 2048;      // columns of the 2x image a CTA stages per lattice row (x 2 rows x 16 B = 64 KB)
+constexpr int kMaxRowPix = 128;      // lattice pixels per row: ceil(span / max(int(span/56),1)) < 112 (dense_align.py:39-45)
+
+// One stage of the depth search for one (RoI, row slice): rows a = slice, slice + nslices, ...  Thread t owns lattice
+// column t % PB and the hypotheses h = t / PB + j * (256 / PB), j < NHG, and keeps their SADs in registers across rows;
+// the CTA writes one partial row [NH costs, valid-pixel count] to `part`.
+template <int NH, int PB>
+__device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, const float* __restrict__ imL,
+                                            const float* __restrict__ imR, const float* __restrict__ rdis,
+                                            float* __restrict__ red /*[8][NH+1]*/, float4* __restrict__ strip /*[2][kStripMax]*/,
+                                            int slice, int nslices, float* __restrict__ part /*[NH+1] global*/) {
+    constexpr int G = 256 / PB;                  // hypothesis groups
+    constexpr int NHG = (NH + G - 1) / G;        // hypotheses per thread
+    __shared__ float s_zf[kMaxRowPix];
+    __shared__ float4 s_L[kMaxRowPix];           // left sample (x, y, z), w = 1 if the pixel is valid
+    __shared__ int s_lo[2], s_hi[2];         // by row parity: a row's reset cannot race the previous row's readers
+    float acc[NHG];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) acc[h] = 0.f;
+    for (int j = 0; j < NHG; ++j) acc[j] = 0.f;
     int cnt = 0;
-    const int total = g.nu * g.nv;
-    for (int q = slice * blockDim.x + threadIdx.x; q < total; q += nslices * blockDim.x) {
-        const int a = q / g.nu, b = q - a * g.nu;
-        const float u = (float)(g.u0 + b * g.su), v = (float)(g.v0 + a * g.sv);
-        float dz;
-        if (!ray_test(g, u, v, k, &dz)) continue;
-        ++cnt;
+    const int tid = threadIdx.x;
+    const int pb = tid % PB, hg = tid / PB;
+    int par = 0;
+    for (int a = slice; a < g.nv; a += nslices, par ^= 1) {
+        const float v = (float)(g.v0 + a * g.sv);
         const float gy = __fdiv_rn(__fsub_rn(v, k.fh2), k.fh2);
-        const float3 L = grid_sample(upL, k.FH, k.FW, __fdiv_rn(__fsub_rn(u, k.fw2), k.fw2), gy);
-        const float zf = __fdiv_rn(dz, k.fb32);
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const float d = __fdiv_rn(1.0f, __fadd_rn(zf, rdis[h]));
-            const float gx = __fdiv_rn(__fsub_rn(__fsub_rn(u, d), k.fw2), k.fw2);
-            const float3 R = grid_sample(upR, k.FH, k.FW, gx, gy);
-            acc[h] += fabsf(__fsub_rn(L.x, R.x)) + fabsf(__fsub_rn(L.y, R.y)) + fabsf(__fsub_rn(L.z, R.z));
+        Samp sy;
+        float wy0, wy1;
+        samp_y(sy, gy, k.FH, &wy0, &wy1);
+        if (tid == 0) { s_lo[par] = 0x7fffffff; s_hi[par] = -1; }
+        __syncthreads();
+        // (a) ray test + left sample + reach of the right-image samples, one thread per lattice pixel
+        if (tid < g.nu) {
+            const float u = (float)(g.u0 + tid * g.su);
+            float dz;
+            float4 Lv = make_float4(0.f, 0.f, 0.f, 0.f);
+            float zf = 0.f;
+            if (ray_test(g, u, v, k, &dz)) {
+                Samp s = sy;
+                samp_x(s, __fdiv_rn(__fsub_rn(u, k.fw2), k.fw2), k.FW);
+                samp_weights(s, wy0, wy1);
+                const float3 L = sample_fly(imL, k, s);
+                Lv = make_float4(L.x, L.y, L.z, 1.f);
+                zf = __fdiv_rn(dz, k.fb32);
+                // d = 1 / (zf + rdis[h]) falls with h: h = 0 reaches furthest left, h = NH-1 furthest right
+                Samp e0 = sy, e1 = sy;
+                samp_x(e0, __fdiv_rn(__fsub_rn(__fsub_rn(u, __fdiv_rn(1.0f, __fadd_rn(zf, rdis[0]))), k.fw2), k.fw2), k.FW);
+                samp_x(e1, __fdiv_rn(__fsub_rn(__fsub_rn(u, __fdiv_rn(1.0f, __fadd_rn(zf, rdis[NH - 1]))), k.fw2), k.fw2), k.FW);
+                atomicMin(&s_lo[par], min(e0.xi0, e1.xi0));
+                atomicMax(&s_hi[par], max(e0.xi0, e1.xi0) + 1);
+                ++cnt;
+            }
+            s_L[tid] = Lv;
+            s_zf[tid] = zf;
         }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        __syncthreads();
+        const int lo = s_lo[par];
+        if (lo == 0x7fffffff) continue;              // no valid pixel in this row (uniform across the CTA)
+        const int hi = min(min(s_hi[par], k.FW - 1), lo + kStripMax - 1);
+        const int len = hi - lo + 1;
+        // (b) the strip of the 2x right image this row can reach, built once
+        for (int i = tid; i < len; i += 256) {
+            strip[i] = up_pixel(imR, k.ug, sy.yi0, lo + i);
+            if (sy.row1) strip[kStripMax + i] = up_pixel(imR, k.ug, sy.yi0 + 1, lo + i);
+        }
+        __syncthreads();
+        // (c) SAD of this thread's hypotheses for its lattice pixel
+        if (pb < g.nu) {
+            const float4 Lv = s_L[pb];
+            if (Lv.w != 0.f) {
+                const float u = (float)(g.u0 + pb * g.su);
+                const float zf = s_zf[pb];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-        float s = warp_sum(acc[h]);
-        if (lane == 0) red[warp * (NH + 1) + h] = s;
-    }
-    {
-        float s = warp_sum((float)cnt);
-        if (lane == 0) red[warp * (NH + 1) + NH] = s;
+                for (int j = 0; j < NHG; ++j) {
+                    const int h = hg + j * G;
+                    if (h < NH) {
+                        const float d = __fdiv_rn(1.0f, __fadd_rn(zf, rdis[h]));
+                        Samp s = sy;
+                        samp_x(s, __fdiv_rn(__fsub_rn(__fsub_rn(u, d), k.fw2), k.fw2), k.FW);
+                        samp_weights(s, wy0, wy1);
+                        float3 R;
+                        const int o = s.xi0 - lo;
+                        if (o >= 0 && o + 1 < len + (s.okx ? 0 : 1)) {
+                            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 ta = strip[o], tb = s.okx ? strip[o + 1] : z4;
+                            const float4 tc = s.row1 ? strip[kStripMax + o] : z4;
+                            const float4 td = (s.row1 && s.okx) ? strip[kStripMax + o + 1] : z4;
+                            R = samp_combine(s, ta, tb, tc, td);
+                        } else {
+                            R = sample_fly(imR, k, s);
+                        }
+                        acc[j] += fabsf(__fsub_rn(Lv.x, R.x)) + fabsf(__fsub_rn(Lv.y, R.y)) + fabsf(__fsub_rn(Lv.z, R.z));
+                    }
+                }
+            }
+        }
+        // (the next row's first barrier orders these strip reads before the next fill)
     }
     __syncthreads();
-    const int nw = blockDim.x >> 5;
-    if (threadIdx.x <= NH) {
+    // reduce over the PB lattice columns: lanes first, then the warps of each hypothesis group
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int WPG = PB / 32;                 // warps per hypothesis group
+#pragma unroll
+    for (int j = 0; j < NHG; ++j) {
+        const float s = warp_sum(acc[j]);
+        if (lane == 0) red[warp * NHG + j] = s;
+    }
+    {
+        const float s = warp_sum((float)cnt);
+        if (lane == 0) red[8 * NHG + warp] = s;
+    }
+    __syncthreads();
+    if (tid < NH) {
+        const int hgi = tid % G, j = tid / G;        // hypothesis tid = hgi + j * G
         float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += red[w * (NH + 1) + threadIdx.x];
-        part[threadIdx.x] = s;
+        for (int w = 0; w < WPG; ++w) s += red[(hgi * WPG + w) * NHG + j];
+        part[tid] = s;
+    }
+    if (tid == NH) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[8 * NHG + w];
+        part[NH] = s;
     }
 }
 
@@ -269,13 +364,14 @@ __device__ __forceinline__ int argmin_partials(const float* __restrict__ part, i
     return bi;
 }
 
-// grid (D, S): S lattice slices per RoI so that a few dozen RoIs still fill the machine
+// grid (D, S): S row slices per RoI so that a few dozen RoIs still fill the machine; dynamic smem = the strip
 template <int STAGE>
 __global__ void __launch_bounds__(256)
-dense_stage_kernel(const float4* __restrict__ upL, const float4* __restrict__ upR, Consts k,
+dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR, Consts k,
                    const float* __restrict__ box_left, const float* __restrict__ keypoints,
                    const float* __restrict__ poses, float* __restrict__ part0 /*[D][S][51]*/,
                    float* __restrict__ part1 /*[D][S][21]*/) {
+    extern __shared__ float4 strip[];        // [2][kStripMax]
     __shared__ RoiCtx g;
     __shared__ float rdis[50];
     __shared__ float red[8 * 51];
@@ -299,7 +395,8 @@ dense_stage_kernel(const float4* __restrict__ upL, const float4* __restrict__ up
     }
     __syncthreads();
     float* part = STAGE == 0 ? part0 + ((size_t)i * S + blockIdx.y) * 51 : part1 + ((size_t)i * S + blockIdx.y) * 21;
-    stage_costs<NH>(g, k, upL, upR, rdis, red, blockIdx.y, S, part);
+    if (g.nu <= 64) stage_costs<NH, 64>(g, k, imL, imR, rdis, red, strip, blockIdx.y, S, part);
+    else stage_costs<NH, 128>(g, k, imL, imR, rdis, red, strip, blockIdx.y, S, part);
 }
 
 // one CTA, one warp per RoI: argmins, outputs, and the reference's "no valid pixel anywhere -> dis_init" early-out
@@ -335,15 +432,13 @@ dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __res
 
 constexpr int kMaxSlices = 8;
 
-struct DaLayout { size_t upL, upR, part0, part1, total; };
+struct DaLayout { size_t part0, part1, total; };
 DaLayout da_layout(int H, int W, int D) {
+    (void)H; (void)W;
     DaLayout l;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
-    size_t px = (size_t)4 * H * W;
     const size_t d = (size_t)(D > 0 ? D : 1);
-    l.upL = take(px * sizeof(float4));
-    l.upR = take(px * sizeof(float4));
     l.part0 = take(d * kMaxSlices * 51 * sizeof(float));
     l.part1 = take(d * kMaxSlices * 21 * sizeof(float));
     l.total = off;
@@ -364,8 +459,6 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     if (workspace_bytes < l.total) return SB_EINVAL;
     char* ws = (char*)workspace;
     cudaStream_t st = sb_cs(stream);
-    float4* upL = (float4*)(ws + l.upL);
-    float4* upR = (float4*)(ws + l.upR);
     float* part0 = (float*)(ws + l.part0);
     float* part1 = (float*)(ws + l.part1);
     // dense_align.py:255-266 (python floats = doubles, cast to fp32 where they meet a tensor)
@@ -383,15 +476,23 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     k.FW = 2 * W;
     k.fw2 = (float)(((double)k.FW - 1.0) / 2.0);
     k.fh2 = (float)(((double)k.FH - 1.0) / 2.0);
-    dim3 ug((k.FW + 255) / 256, k.FH, 2);
-    upsample2x_kernel<<<ug, 256, 0, st>>>(im_left, im_right, H, W, upL, upR);
-    SB_LAUNCHED();
-    SB_CHECK_LAUNCH();
+    k.ug.H = H;
+    k.ug.W = W;
+    k.ug.rh = (float)(H - 1) / (float)(k.FH - 1);       // F.upsample(align_corners=True) source ratios, fp32 division
+    k.ug.rw = (float)(W - 1) / (float)(k.FW - 1);
+    constexpr size_t kStripBytes = (size_t)2 * kStripMax * sizeof(float4);
+    static bool attr_done[kSbMaxDevices] = {false};
+    if (!attr_done[sb_cur_device()]) {
+        cudaError_t e = cudaFuncSetAttribute(dense_stage_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStripBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStripBytes);
+        if (e != cudaSuccess) return (int)e;
+        attr_done[sb_cur_device()] = true;
+    }
     int S = 296 / D;                  // two waves of 148 SMs worth of CTAs
     S = S < 1 ? 1 : (S > kMaxSlices ? kMaxSlices : S);
-    dense_stage_kernel<0><<<dim3(D, S), 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, part0, part1);
+    dense_stage_kernel<0><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, part0, part1);
     SB_LAUNCHED();
-    dense_stage_kernel<1><<<dim3(D, S), 256, 0, st>>>(upL, upR, k, box_left, keypoints, poses, part0, part1);
+    dense_stage_kernel<1><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, part0, part1);
     SB_LAUNCHED();
     dense_final_kernel<<<1, 256, 0, st>>>(k, poses, part0, part1, D, S, status, best_dis);
     SB_LAUNCHED();
