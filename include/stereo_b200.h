@@ -209,6 +209,34 @@ int sb_fill(float* p, size_t n, float v, sb_stream_t stream);
 /* number of kernel launches issued by this library since load (bench "gpu_launches") */
 unsigned long long sb_launch_count(void);
 
+/* ------------------------------------------------- 3D box solvers ----
+ * The CPU stage between the network and dense_align (test_net.py:262-325), on the device.
+ * sb_infer_boundary: kitti_utils.infer_boundary (kitti_utils.py:398-437) over the kept detections (keep[0..*num),
+ *   in kept order); boxes [R, ld] with the box at column col_offset; left_right [>= *num, 2].
+ * sb_box_solve: the keypoint border fix-up (test_net.py:263-266, inferred may be NULL) and
+ *   box_estimator.solve_x_y_z_theta_from_kpt (box_estimator.py:169-385) per kept detection of class `cls` with
+ *   score > eval_thresh; solved detections are appended in order to boxes_all [cap,5] (box + score), kpts_all
+ *   [cap,5], poses_all [cap,8] (x,y,z,w,h,l,theta,alpha) as test_net.py:281-303 builds them; src_index [cap] = RoI
+ *   index, *n_out (device) = how many.  p2 / p3: 3x4 row-major projection matrices, (im_h, im_w) the ORIGINAL image.
+ * sb_dense_align_n: sb_dense_align on those device-resident rows (count read on the device).
+ * sb_box_rectify: box_estimator.solve_x_y_theta_from_kpt (box_estimator.py:387-545) with the aligned disparity ->
+ *   final [cap,13] doubles: valid, score, box_left[4], x, y, z, w, h, l, theta (what write_detection_results takes).
+ * The reference minimises with scipy Newton-CG; here Levenberg-Marquardt in fp64 on the same residuals, to a
+ * tighter stationarity than Newton-CG's own end points (tests/test_box_solver.py).                              */
+int sb_infer_boundary(const float* boxes, int ld, int col_offset, const int* keep, const int* num, int im_w,
+                      float* left_right, sb_stream_t stream);
+int sb_box_solve(const float* scores, const float* boxes_left, const float* boxes_right, const float* dim_orien,
+                 const float* kpts, const int* keep, const int* num, const float* inferred, int n_classes, int cls,
+                 int im_h, int im_w, const double* p2, const double* p3, float eval_thresh, int cap,
+                 float* boxes_all, float* kpts_all, float* poses_all, int* src_index, int* n_out, sb_stream_t stream);
+int sb_dense_align_n(const float* im_left, const float* im_right, int H, int W, const double* calib4, double scale,
+                     const float* box_left, int box_ld, const float* keypoints, const float* poses, int pose_ld,
+                     int D_cap, const int* n_dev, float* status, float* best_dis, void* workspace,
+                     size_t workspace_bytes, sb_stream_t stream);
+int sb_box_rectify(const float* boxes_all, const float* kpts_all, const float* poses_all, const float* succ,
+                   const float* best_dis, const int* n, int cap, int im_h, int im_w, const double* p2,
+                   const double* p3, double* final_out, sb_stream_t stream);
+
 /* ------------------------------------------------- record all-gather over peer memory ----
  * The path's only exchange: every rank's fixed-size detection record ([300, 15nc+5] fp32, ~40 KB) to every rank of
  * one NVSwitch box.  Each rank owns a mailbox (sb_peer_alloc), exports it with CUDA IPC (sb_ipc_export, 64-byte

@@ -190,8 +190,9 @@ def infer_boundary(im_shape, boxes_left):
     n = boxes_left.shape[0]
     left_right = np.zeros((n, 2), dtype=np.float32)
     depth_line = np.zeros(im_shape[1] + 1, dtype=float)
+    # (under the reference's numpy 1.x, `1050.0 / np.float32` is a float64: restated with float())
     for i in range(n):
-        depth = 1050.0 / boxes_left[i, 3]
+        depth = 1050.0 / float(boxes_left[i, 3])
         for col in range(int(boxes_left[i, 0]), int(boxes_left[i, 2]) + 1):
             pixel = depth_line[col]
             if pixel == 0.0:
@@ -199,7 +200,7 @@ def infer_boundary(im_shape, boxes_left):
             elif depth < depth_line[col]:
                 depth_line[col] = (depth + pixel) / 2.0
     for i in range(n):
-        depth = 1050.0 / boxes_left[i, 3]
+        depth = 1050.0 / float(boxes_left[i, 3])
         left_right[i, 0], left_right[i, 1] = boxes_left[i, 0], boxes_left[i, 2]
         left_visible = not depth_line[int(boxes_left[i, 0])] < depth
         right_visible = not depth_line[int(boxes_left[i, 2])] < depth

@@ -369,16 +369,17 @@ template <int STAGE>
 __global__ void __launch_bounds__(256)
 dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR, Consts k,
                    const float* __restrict__ box_left, const float* __restrict__ keypoints,
-                   const float* __restrict__ poses, float* __restrict__ part0 /*[D][S][51]*/,
-                   float* __restrict__ part1 /*[D][S][21]*/) {
+                   const float* __restrict__ poses, int box_ld, int pose_ld, float* __restrict__ part0 /*[D][S][51]*/,
+                   float* __restrict__ part1 /*[D][S][21]*/, const int* __restrict__ n_dev) {
     extern __shared__ float4 strip[];        // [2][kStripMax]
+    if (n_dev && (int)blockIdx.x >= *n_dev) return;      // device-side RoI count (the solver's output): CTA-uniform
     __shared__ RoiCtx g;
     __shared__ float rdis[50];
     __shared__ float red[8 * 51];
     __shared__ float best_depth;
     __shared__ int best_idx;
     const int i = blockIdx.x, S = gridDim.y;
-    if (threadIdx.x == 0) setup_roi(box_left + 4 * i, keypoints + 5 * i, poses + 7 * i, k, &g);
+    if (threadIdx.x == 0) setup_roi(box_left + (size_t)box_ld * i, keypoints + 5 * i, poses + (size_t)pose_ld * i, k, &g);
     if (STAGE == 1 && threadIdx.x >= 32 && threadIdx.x < 64) {      // warp 1, concurrently with the box setup
         const int bi = argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, nullptr);
         if (threadIdx.x == 32) best_idx = bi;
@@ -401,15 +402,16 @@ dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR,
 
 // one CTA, one warp per RoI: argmins, outputs, and the reference's "no valid pixel anywhere -> dis_init" early-out
 __global__ void __launch_bounds__(256)
-dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __restrict__ part0,
+dense_final_kernel(Consts k, const float* __restrict__ poses, int pose_ld, const float* __restrict__ part0,
                    const float* __restrict__ part1, int D, int S, float* __restrict__ status,
-                   float* __restrict__ best_dis) {
+                   float* __restrict__ best_dis, const int* __restrict__ n_dev) {
     __shared__ int any_valid;
+    if (n_dev) D = min(D, *n_dev);
     if (threadIdx.x == 0) any_valid = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int i = warp; i < D; i += nw) {
-        const float dis_init = __fdiv_rn(k.fb32, poses[7 * i + 2]);
+        const float dis_init = __fdiv_rn(k.fb32, poses[(size_t)pose_ld * i + 2]);
         const float z0 = __fmul_rn(__fmul_rn(__fdiv_rn(1.0f, dis_init), k.f32), k.bl32);
         float npix;
         const float bd0 = coarse_depth(z0, argmin_partials(part0 + (size_t)i * S * 51, S, 50, 51, &npix));
@@ -425,7 +427,7 @@ dense_final_kernel(Consts k, const float* __restrict__ poses, const float* __res
     if (!any_valid) {   // dense_align.py:272-273
         for (int i = threadIdx.x; i < D; i += blockDim.x) {
             status[i] = 0.f;
-            best_dis[i] = __fdiv_rn(k.fb32, poses[7 * i + 2]);
+            best_dis[i] = __fdiv_rn(k.fb32, poses[(size_t)pose_ld * i + 2]);
         }
     }
 }
@@ -449,10 +451,34 @@ DaLayout da_layout(int H, int W, int D) {
 
 extern "C" size_t sb_dense_align_workspace_bytes(int H, int W, int D) { return da_layout(H, W, D).total; }
 
+static int dense_align_impl(const float* im_left, const float* im_right, int H, int W, const double* calib4,
+                            double scale, const float* box_left, int box_ld, const float* keypoints, const float* poses,
+                            int pose_ld, int D, const int* n_dev, float* status, float* best_dis, void* workspace,
+                            size_t workspace_bytes, sb_stream_t stream);
+
 extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H, int W, const double* calib4,
                               double scale, const float* box_left, const float* keypoints, const float* poses,
                               int D, float* status, float* best_dis, void* workspace, size_t workspace_bytes,
                               sb_stream_t stream) {
+    return dense_align_impl(im_left, im_right, H, W, calib4, scale, box_left, 4, keypoints, poses, 7, D, nullptr, status,
+                            best_dis, workspace, workspace_bytes, stream);
+}
+
+// D_cap rows are launched; rows >= *n_dev (a device-resident count, e.g. sb_box_solve's n_out) do no work and get no
+// output.  box / pose rows may be wider than 4 / 7 floats (boxes_all [cap,5], poses_all [cap,8] of the solver).
+extern "C" int sb_dense_align_n(const float* im_left, const float* im_right, int H, int W, const double* calib4,
+                                double scale, const float* box_left, int box_ld, const float* keypoints,
+                                const float* poses, int pose_ld, int D_cap, const int* n_dev, float* status,
+                                float* best_dis, void* workspace, size_t workspace_bytes, sb_stream_t stream) {
+    if (!n_dev || box_ld < 4 || pose_ld < 7) return SB_EINVAL;
+    return dense_align_impl(im_left, im_right, H, W, calib4, scale, box_left, box_ld, keypoints, poses, pose_ld, D_cap,
+                            n_dev, status, best_dis, workspace, workspace_bytes, stream);
+}
+
+static int dense_align_impl(const float* im_left, const float* im_right, int H, int W, const double* calib4,
+                            double scale, const float* box_left, int box_ld, const float* keypoints, const float* poses,
+                            int pose_ld, int D, const int* n_dev, float* status, float* best_dis, void* workspace,
+                            size_t workspace_bytes, sb_stream_t stream) {
     if (D == 0) return SB_OK;
     if (D < 0 || H < 2 || W < 2 || !im_left || !im_right || !calib4 || !workspace) return SB_EINVAL;
     DaLayout l = da_layout(H, W, D);
@@ -490,11 +516,11 @@ extern "C" int sb_dense_align(const float* im_left, const float* im_right, int H
     }
     int S = 296 / D;                  // two waves of 148 SMs worth of CTAs
     S = S < 1 ? 1 : (S > kMaxSlices ? kMaxSlices : S);
-    dense_stage_kernel<0><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, part0, part1);
+    dense_stage_kernel<0><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
     SB_LAUNCHED();
-    dense_stage_kernel<1><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, part0, part1);
+    dense_stage_kernel<1><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
     SB_LAUNCHED();
-    dense_final_kernel<<<1, 256, 0, st>>>(k, poses, part0, part1, D, S, status, best_dis);
+    dense_final_kernel<<<1, 256, 0, st>>>(k, poses, pose_ld, part0, part1, D, S, status, best_dis, n_dev);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

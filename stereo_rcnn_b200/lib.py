@@ -57,6 +57,14 @@ _SIGS = {
     "sb_dense_align": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_double), c_double,
                                c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
+    "sb_dense_align_n": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_double), c_double, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    "sb_infer_boundary": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "sb_box_solve": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, ctypes.POINTER(c_double),
+                             ctypes.POINTER(c_double), c_float, c_int] + [c_void_p] * 5 + [c_void_p]),
+    "sb_box_rectify": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, ctypes.POINTER(c_double),
+                               ctypes.POINTER(c_double), c_void_p, c_void_p]),
     "sb_conv2d_simt": (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
     "sb_conv2d_tc": (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
     "sb_conv2d_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),

@@ -222,6 +222,89 @@ def dense_align(calib4, scale, im_left, im_right, box_left, keypoints, poses):
     return status, best
 
 
+def dense_align_n(calib4, scale, im_left, im_right, boxes_all, keypoints, poses_all, n_dev):
+    """align_parallel on device-resident solver outputs: boxes_all [cap,>=4], keypoints [cap,5], poses_all [cap,>=7],
+    n_dev int32 [1] (how many rows are live) -> status [cap], best_dis [cap]; rows >= n are left at zero"""
+    L = _l.load()
+    iml = _f32c(im_left).reshape(3, *im_left.shape[-2:])
+    imr = _f32c(im_right).reshape(3, *im_right.shape[-2:])
+    H, W = iml.shape[1:]
+    cap = boxes_all.shape[0]
+    dev = iml.device
+    status = torch.zeros(cap, dtype=torch.float32, device=dev)
+    best = torch.zeros(cap, dtype=torch.float32, device=dev)
+    nb = L.sb_dense_align_workspace_bytes(H, W, cap)
+    ws = workspace(nb, dev, "dense_align")
+    c4 = (ctypes.c_double * 4)(*[float(v) for v in calib4])
+    check(L.sb_dense_align_n(ptr(iml), ptr(imr), H, W, c4, float(scale), ptr(_f32c(boxes_all)), boxes_all.shape[1],
+                             ptr(_f32c(keypoints)), ptr(_f32c(poses_all)), poses_all.shape[1], cap, ptr(n_dev),
+                             ptr(status), ptr(best), ptr(ws), nb, stream_ptr()), "sb_dense_align_n")
+    return status, best
+
+
+# ------------------------------------------------------------ box solver ----
+def _p34(p):
+    return (ctypes.c_double * 12)(*[float(v) for v in np.asarray(p, np.float64).reshape(-1)])
+
+
+def infer_boundary(boxes, keep, num, im_w, col_offset=0):
+    """kitti_utils.infer_boundary (kitti_utils.py:398-437) over boxes[keep[:num]] -> left_right [R,2] (kept order)"""
+    L = _l.load()
+    R = boxes.shape[0]
+    out = torch.zeros(R, 2, dtype=torch.float32, device=boxes.device)
+    check(L.sb_infer_boundary(ptr(_f32c(boxes)), boxes.shape[1], int(col_offset), ptr(keep), ptr(num), int(im_w),
+                              ptr(out), stream_ptr()), "sb_infer_boundary")
+    return out
+
+
+def box_solve(scores, boxes_left, boxes_right, dim_orien, kpts, keep, num, im_hw, p2, p3, cls=1, eval_thresh=0.05,
+              inferred=None, cap=None):
+    """test_net.py:263-303 on the device: border fix-up + solve_x_y_z_theta_from_kpt per kept detection, solved ones
+    appended in order -> boxes_all [cap,5], kpts_all [cap,5], poses_all [cap,8], src_index [cap], n [1] (device)"""
+    L = _l.load()
+    R, nc = scores.shape
+    cap = R if cap is None else int(cap)
+    dev = scores.device
+    boxes_all = torch.zeros(cap, 5, dtype=torch.float32, device=dev)
+    kpts_all = torch.zeros(cap, 5, dtype=torch.float32, device=dev)
+    poses_all = torch.zeros(cap, 8, dtype=torch.float32, device=dev)
+    src = torch.zeros(cap, dtype=torch.int32, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(L.sb_box_solve(ptr(_f32c(scores)), ptr(_f32c(boxes_left)), ptr(_f32c(boxes_right)), ptr(_f32c(dim_orien)),
+                         ptr(_f32c(kpts)), ptr(keep), ptr(num), ptr(inferred), nc, int(cls), int(im_hw[0]),
+                         int(im_hw[1]), _p34(p2), _p34(p3), float(eval_thresh), cap, ptr(boxes_all), ptr(kpts_all),
+                         ptr(poses_all), ptr(src), ptr(n), stream_ptr()), "sb_box_solve")
+    return boxes_all, kpts_all, poses_all, src, n
+
+
+def box_rectify(boxes_all, kpts_all, poses_all, succ, best_dis, n, im_hw, p2, p3):
+    """test_net.py:311-325: solve_x_y_theta_from_kpt with the aligned disparity -> final [cap,13] float64
+    (valid, score, box_left 4, x, y, z, w, h, l, theta)"""
+    L = _l.load()
+    cap = boxes_all.shape[0]
+    out = torch.zeros(cap, 13, dtype=torch.float64, device=boxes_all.device)
+    check(L.sb_box_rectify(ptr(boxes_all), ptr(kpts_all), ptr(poses_all), ptr(succ), ptr(best_dis), ptr(n), cap,
+                           int(im_hw[0]), int(im_hw[1]), _p34(p2), _p34(p3), ptr(out), stream_ptr()), "sb_box_rectify")
+    return out
+
+
+def kitti_result_lines(final, t_cam2_cam0_x):
+    """kitti_utils.write_detection_results' text (kitti_utils.py:440-460) for the valid rows of box_rectify's output
+    (host side: formatting text is not device work)"""
+    import math
+    lines = []
+    for r in final.detach().cpu().numpy():
+        if r[0] <= 0:
+            continue
+        score, box, pos, dim, orien = r[1], r[2:6], r[6:9], r[9:12], r[12]
+        alpha = orien - math.pi / 2 + math.atan2(-pos[0], pos[2])
+        s = "Car -1 -1 "
+        s += "%f %f %f %f %f " % (alpha, box[0], box[1], box[2], box[3])
+        s += "%f %f %f %f %f %f %f %f \n" % (dim[1], dim[0], dim[2], pos[0] - t_cam2_cam0_x, pos[1], pos[2], orien - 1.57, score)
+        lines.append(s)
+    return lines
+
+
 # ------------------------------------------------------------- layer ops ----
 def conv_desc(x, wgt, out, Cin, Cout, kh, kw, stride, pad, Ho, Wo, scale=None, shift=None, residual=None,
               up_src=None, relu=False, in_ld=None, out_coff=0, out_strides=None, out_mode=0, res_biased=False,

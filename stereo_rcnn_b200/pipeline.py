@@ -80,6 +80,32 @@ class StereoPipeline(object):
         return record, keep, nkeep, st, dis
 
 
+    def step_with_solver(self, iml, imr, p2, p3, im_hw_orig, cls=1, eval_thresh=0.05, cap=None):
+        """One pair (B = 1) end to end as test_net.py:120-330 runs it, with the solver stage on the device:
+        forward -> decode (+ record) -> per-class NMS -> infer_boundary + border fix-up ->
+        solve_x_y_z_theta_from_kpt -> dense_align on the solved poses -> solve_x_y_theta_from_kpt.
+        No host synchronisation: detection counts stay on the device (graph-capturable).
+        -> dict(record [300,33], keep, nkeep, n_solved [1], boxes_all, poses_all, status, best_dis, final [cap,13])"""
+        assert iml.shape[0] == 1
+        _, _, H, W = iml.shape
+        info = self.im_info(1, H, W)
+        o = self.eng.forward(iml, imr, info)
+        R = o["rois_left"].shape[1]
+        pbl, pbr, do, pk, rec = ops.test_decode_record(
+            o["rois_left"][0], o["rois_right"][0], o["cls_prob"][0], o["bbox_pred"][0], o["dim_orien_pred"][0],
+            o["kpts_prob"], o["left_border_prob"], o["right_border_prob"], info[0], n_classes=N_CLASSES)
+        keep, nkeep = ops.class_nms(o["cls_prob"][0], pbl, cls, eval_thresh, 0.3)
+        inferred = ops.infer_boundary(pbl, keep, nkeep, im_hw_orig[1], col_offset=4 * cls)
+        boxes_all, kpts_all, poses_all, src, n = ops.box_solve(
+            o["cls_prob"][0], pbl, pbr, do, pk, keep, nkeep, im_hw_orig, p2, p3, cls=cls, eval_thresh=eval_thresh,
+            inferred=inferred, cap=cap or R)
+        calib4 = ops.calib_vec(p2, p3)
+        st, dis = ops.dense_align_n(calib4, self.scale, iml[0], imr[0], boxes_all, kpts_all, poses_all, n)
+        final = ops.box_rectify(boxes_all, kpts_all, poses_all, st, dis, n, im_hw_orig, p2, p3)
+        return dict(record=rec, keep=keep, nkeep=nkeep, n_solved=n, boxes_all=boxes_all, kpts_all=kpts_all,
+                    poses_all=poses_all, src_index=src, status=st, best_dis=dis, final=final)
+
+
 class GraphSlot(object):
     """One in-flight step: fixed device inputs, private workspaces, own stream, CUDA graph of `pipe.step`.
 

@@ -64,9 +64,76 @@ def demo_goldens():
     print("demo goldens written")
 
 
+def solver_goldens():
+    """(10) the reference's own box solvers / infer_boundary / result writer (box_estimator.py, kitti_utils.py), executed
+    from the files where they lie with two runtime patches (py2 implicit import, `scipy.array` removed from scipy)."""
+    import math as m
+    import tempfile
+    import types
+    src = open(os.path.join(ref_shim.REF, "lib/model/utils/box_estimator.py")).read()
+    src = src.replace("import kitti_utils as utils", "utils = None").replace("scipy.array", "np.array")
+    be = types.ModuleType("box_estimator")
+    exec(compile(src, "box_estimator.py", "exec"), be.__dict__)
+    ku = types.ModuleType("kitti_utils")
+    exec(compile(open(os.path.join(ref_shim.REF, "lib/model/utils/kitti_utils.py")).read(), "kitti_utils.py", "exec"), ku.__dict__)
+    calib = ref_shim.demo_calib()
+    P2, P3 = calib.p2, calib.p3
+    f32 = np.float32
+    b, k, p = gen_rois(64, seed=7, p2=P2)
+    rs = np.random.RandomState(1)
+    rows = dict(alpha=[], dim=[], box_left=[], box_right=[], kpts=[], status=[], state=[], disparity=[], state_rect=[], z_rect=[])
+    shape = (375, 1242, 3)
+    for i in range(64):
+        x, y, z, w, h, l, th = [float(v) for v in p[i]]
+        bl = (P2[0, 3] - P3[0, 3]) / P2[0, 0]
+        disp = P2[0, 0] * bl / z
+        box_l = b[i].astype(np.float64)
+        if i % 8 == 7:          # a truncated detection (left border)
+            box_l[0] = 5.0
+        box_r = box_l.copy()
+        box_r[[0, 2]] -= disp
+        box_r += rs.randn(4) * 0.5
+        kt = int(rs.randint(0, 4))
+        vw, vl = [(-w, -l), (-w, l), (w, l), (w, -l)][kt]
+        X = x + np.cos(th) * vw / 2 + np.sin(th) * vl / 2
+        Z = z - np.sin(th) * vw / 2 + np.cos(th) * vl / 2
+        kp = np.array([P2[0, 0] * X / Z + P2[0, 2], kt, 0.9, box_l[0], box_l[2]])
+        alpha = th - m.pi / 2 + m.atan2(-x, z) + rs.randn() * 0.05
+        dim = np.array([w, h, l]) + rs.randn(3) * 0.05
+        # everything reaches the solvers as float32 tensor elements in test_net.py
+        box_l, box_r, kp, dim, alpha = [np.asarray(v, f32).astype(np.float64) for v in (box_l, box_r, kp, dim, alpha)]
+        st, s = be.solve_x_y_z_theta_from_kpt(shape, calib, float(alpha), dim, box_l, box_r, kp)
+        s = np.zeros(4) if np.isscalar(s) else np.asarray(s, np.float64)
+        disp2 = float(f32(disp + rs.randn() * 0.3))
+        s3, z3 = be.solve_x_y_theta_from_kpt(shape, calib, float(alpha), dim, box_l, disp2, kp)
+        for key, v in (("alpha", alpha), ("dim", dim), ("box_left", box_l), ("box_right", box_r), ("kpts", kp),
+                       ("status", st), ("state", s), ("disparity", disp2), ("state_rect", np.asarray(s3)), ("z_rect", z3)):
+            rows[key].append(v)
+    # infer_boundary on overlapping detections (kept order)
+    rs = np.random.RandomState(4)
+    x1 = rs.rand(24) * 1000
+    y1 = rs.rand(24) * 200
+    ib_boxes = np.stack([x1, y1, np.minimum(x1 + 30 + rs.rand(24) * 300, 1241), np.minimum(y1 + 30 + rs.rand(24) * 140, 374),
+                         rs.rand(24)], 1).astype(f32)
+    ib = ku.infer_boundary(shape, ib_boxes)
+    # write_detection_results
+    tmp = tempfile.mkdtemp()
+    calib.t_cam2_cam0 = np.array([(P2[0, 3] - 0.0) / P2[0, 0], 0.0, 0.0])
+    ku.write_detection_results(tmp, "000001", calib, rows["box_left"][0], np.array([1.5, 1.6, 20.25]),
+                               np.array([1.6, 1.5, 3.9]), 0.3, 0.87)
+    line = open(os.path.join(tmp, "data", "000001.txt")).read()
+    np.savez_compressed(os.path.join(HERE, "box_solver.npz"), p2=P2, p3=P3, im_shape=np.array(shape),
+                        **{k_: np.array(v) for k_, v in rows.items()}, ib_boxes=ib_boxes, ib_left_right=ib,
+                        t_cam2_cam0_x=calib.t_cam2_cam0[0], kitti_line=np.array(line),
+                        kitti_args=np.array([1.5, 1.6, 20.25, 1.6, 1.5, 3.9, 0.3, 0.87]))
+    print("solver goldens written")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "demo":
         return demo_goldens()
+    if len(sys.argv) > 1 and sys.argv[1] == "solver":
+        return solver_goldens()
     ref = ref_shim.load()
     cfg = ref.cfg
     calib = ref_shim.demo_calib()
@@ -197,6 +264,7 @@ def main():
                         score_thresh=0.05, nms_thresh=float(cfg.TEST.NMS), kept_rois=kept_rois,
                         cls_dets_left=ns2["cls_dets_left"].numpy(), cls_kpts=ns2["cls_kpts"].numpy())
     demo_goldens()
+    solver_goldens()
     print("goldens written to", HERE)
 
 

@@ -1,0 +1,128 @@
+"""CPU: the 3D box solvers.
+
+* the oracle (oracle/box_solver.py: the reference's objective / gradient restated, scipy Newton-CG) against goldens
+  minted from the reference's own box_estimator.py / kitti_utils.py (tests/golden/make_golden.py (10));
+* the PRODUCT's solver numerics (stereo_rcnn_b200/csrc/box_solver_core.h, the code the device kernels run) compiled
+  for the host with g++: objective and gradient identical to the reference's, and its Levenberg-Marquardt end points
+  at least as stationary as the reference's scipy end points.
+
+Newton-CG stops on a step-size test; on these weakly constrained problems (depth from a box height) its end point
+moves by centimetres to metres when its inputs change in the last bit -- two scipy runs on bit-identical f / grad
+already differ (see the test).  "Parity within solver tolerance" is therefore stated on the objective: at our
+solution the reference's own gradient is smaller than at the reference's solution, and the objective is not larger.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import box_solver as BS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "box_solver.npz"))
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("boxhost") / "libboxhost.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests/tools/box_solver_host.cpp")])
+    return ctypes.CDLL(so)
+
+
+def P(a):
+    a = np.ascontiguousarray(a, np.float64)
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), a
+
+
+def test_oracle_objective_and_solutions_vs_reference(gold):
+    g = gold
+    shape = tuple(int(v) for v in g["im_shape"])
+    n_same = 0
+    for i in range(len(g["alpha"])):
+        if int(g["status"][i]) == 0 and not g["state"][i].any():
+            st, _ = BS.solve_x_y_z_theta_from_kpt(shape, g["p2"], g["p3"], g["alpha"][i], g["dim"][i], g["box_left"][i],
+                                                  g["box_right"][i], g["kpts"][i])
+            assert st == 0
+            continue
+        pb = BS.Problem(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i], g["box_right"][i], g["kpts"][i])
+        st, s = BS.solve_x_y_z_theta_from_kpt(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i],
+                                              g["box_right"][i], g["kpts"][i])
+        # same function: the reference's end point is (nearly) stationary for the restated gradient too
+        assert np.abs(pb.gradient(g["state"][i])).max() < 5e-3
+        n_same += np.abs(np.asarray(s) - g["state"][i]).max() < 1e-3
+        s3, z3 = BS.solve_x_y_theta_from_kpt(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i],
+                                             float(g["disparity"][i]), g["kpts"][i])
+        assert abs(z3 - float(g["z_rect"][i])) < 1e-12 * abs(z3)
+        pr = BS.Problem(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i], None, g["kpts"][i], z_fixed=z3)
+        assert np.abs(pr.gradient(g["state_rect"][i])).max() < 5e-3
+    # scipy on bit-identical f / grad reproduces only part of the reference's end points: the documented instability
+    assert n_same >= 10
+
+
+def test_infer_boundary_and_kitti_line_vs_reference(gold):
+    g = gold
+    lr = BS.infer_boundary(tuple(int(v) for v in g["im_shape"]), g["ib_boxes"])
+    np.testing.assert_array_equal(lr, g["ib_left_right"])
+    a = g["kitti_args"]
+    line = BS.kitti_result_line(float(g["t_cam2_cam0_x"]), g["box_left"][0], a[0:3], a[3:6], a[6], a[7])
+    assert line == str(g["kitti_line"])
+
+
+def _solve(host_lib, g, i, rect):
+    s, info = np.zeros(4), np.zeros(4)
+    args = [P(g["p2"]), P(g["p3"]), None, P(g["dim"][i]), P(g["box_left"][i]), P(g["box_right"][i]), P(g["kpts"][i])]
+    host_lib.box_solve_host(int(g["im_shape"][0]), int(g["im_shape"][1]), args[0][0], args[1][0],
+                            ctypes.c_double(float(g["alpha"][i])), args[3][0], args[4][0], args[5][0], args[6][0],
+                            int(rect), ctypes.c_double(float(g["disparity"][i]) if rect else 0.0),
+                            s.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                            info.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return s, info
+
+
+def test_product_solver_core_vs_reference(gold, host_lib):
+    """box_solver_core.h on the host: (1) f and the reference-style gradient equal the oracle's at the reference's end
+    points; (2) the LM end points are more stationary than the reference's and not worse in objective"""
+    g = gold
+    shape = tuple(int(v) for v in g["im_shape"])
+    fo, g4 = ctypes.c_double(), np.zeros(4)
+    worse, n, dz = 0, 0, []
+    for i in range(len(g["alpha"])):
+        if int(g["status"][i]) == 0 and not g["state"][i].any():
+            continue
+        pb = BS.Problem(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i], g["box_right"][i], g["kpts"][i])
+        sref = g["state"][i]
+        a = [P(g["p2"]), P(g["p3"]), P(g["dim"][i]), P(g["box_left"][i]), P(g["box_right"][i]), P(g["kpts"][i]), P(sref)]
+        host_lib.box_eval_host(shape[0], shape[1], a[0][0], a[1][0], ctypes.c_double(float(g["alpha"][i])), a[2][0], a[3][0],
+                               a[4][0], a[5][0], 0, ctypes.c_double(0.0), a[6][0], ctypes.byref(fo),
+                               g4.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert abs(fo.value - pb.objective(sref)) <= 1e-14 * (1 + abs(fo.value))
+        np.testing.assert_allclose(g4, pb.gradient(sref), rtol=1e-10, atol=1e-14)
+        s, info = _solve(host_lib, g, i, False)
+        assert np.abs(pb.gradient(s)).max() < 1e-8, (i, pb.gradient(s))                 # stationary for the reference's gradient
+        assert np.abs(pb.gradient(s)).max() <= np.abs(pb.gradient(sref)).max() + 1e-12
+        n += 1
+        # minimised function: sum r_i^2 with the keypoint residual weighted sqrt(2) (what j_kpt is the gradient of)
+        def f_eff(st, pb_=pb):
+            r, _ = pb_.residuals(st)
+            r = r.copy(); r[2] /= np.sqrt(2.0)
+            return float(np.dot(r, r))
+        worse += f_eff(s) > f_eff(sref) + 1e-12
+        dz.append(np.abs(s - sref).max())
+        # rectification solve (z fixed)
+        s3, _ = _solve(host_lib, g, i, True)
+        pr = BS.Problem(shape, g["p2"], g["p3"], float(g["alpha"][i]), g["dim"][i], g["box_left"][i], None, g["kpts"][i],
+                        z_fixed=float(g["z_rect"][i]))
+        assert abs(s3[2] - float(g["z_rect"][i])) < 1e-12 * abs(s3[2])
+        ours = s3[[0, 1, 3]]
+        assert np.abs(pr.gradient(ours)).max() < 1e-8
+        assert np.abs(pr.gradient(ours)).max() <= np.abs(pr.gradient(g["state_rect"][i])).max() + 1e-12
+    assert n >= 40
+    assert worse <= 0.1 * n, "LM ended in a worse basin than Newton-CG in %d of %d cases" % (worse, n)
+    print("median |state - reference state| = %.3g, 90th pct %.3g (Newton-CG's own end points are unstable at this level)"
+          % (np.median(dz), np.percentile(dz, 90)))

@@ -351,3 +351,98 @@ def test_record_gather_and_shard_equivalence_on_hardware(mode):
     for rank, m, ok, _d in res:
         assert ok, "rank %d: gathered records differ" % rank
         assert m == mode, "requested %s, ran %s" % (mode, res[0][3])
+
+
+# ------------------------------------------------------------------ 8f-1: box solvers on the device
+def test_box_solver_device_chain_vs_oracle(golden_dir):
+    """infer_boundary -> border fix-up -> solve_x_y_z_theta -> (dense_align) -> solve_x_y_theta on the device against
+    the oracle's restatement of the reference: indices / boundaries exact, solver end points stationary for the
+    reference's own gradient (tests/test_box_solver.py explains why end points are not compared digit by digit)"""
+    from oracle import box_solver as BS
+    g = np.load(os.path.join(golden_dir, "box_solver.npz"))
+    shape = tuple(int(v) for v in g["im_shape"])
+    n = len(g["alpha"])
+    R, nc = 80, 2
+    rs = np.random.RandomState(11)
+    scores = np.zeros((R, nc), np.float32)
+    pbl, pbr = np.zeros((R, 8), np.float32), np.zeros((R, 8), np.float32)
+    do, pk = np.zeros((R, 10), np.float32), np.zeros((R, 5), np.float32)
+    rows = rs.permutation(R)[:n]                      # detections scattered over the RoI rows
+    sc = np.sort(rs.rand(n).astype(np.float32) * 0.9 + 0.06)[::-1]
+    for j, r in enumerate(rows):
+        scores[r, 1] = sc[j]
+        pbl[r, 4:8], pbr[r, 4:8] = g["box_left"][j], g["box_right"][j]
+        do[r, 5:8] = g["dim"][j]
+        do[r, 8], do[r, 9] = np.sin(g["alpha"][j]), np.cos(g["alpha"][j])
+        pk[r] = g["kpts"][j]
+    keep = np.zeros(R, np.int32)
+    keep[:n] = rows                                   # kept order = score order
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    keep_d, num_d = c(keep), c(np.array([n], np.int32))
+    inf = G.infer_boundary(c(pbl), keep_d, num_d, shape[1], col_offset=4)
+    inf_ref = BS.infer_boundary(shape, pbl[rows, 4:8])
+    np.testing.assert_array_equal(inf[:n].cpu().numpy(), inf_ref)
+    boxes_all, kpts_all, poses_all, src, nd = G.box_solve(c(scores), c(pbl), c(pbr), c(do), c(pk), keep_d, num_d, shape[:2],
+                                                         g["p2"], g["p3"], inferred=inf)
+    torch.cuda.synchronize()
+    ns = int(nd[0])
+    src = src[:ns].cpu().numpy()
+    poses = poses_all[:ns].cpu().numpy().astype(np.float64)
+    kall = kpts_all[:ns].cpu().numpy()
+    # every solved detection, in kept order; unsolved ones are exactly the reference's status-0 rules
+    pos = {int(r): j for j, r in enumerate(rows)}
+    last = -1
+    for q in range(ns):
+        j = pos[int(src[q])]
+        assert j > last
+        last = j
+        kp = pk[rows[j]].copy()
+        if kp[4] - kp[3] < np.float32(0.5) * (inf_ref[j, 1] - inf_ref[j, 0]):
+            kp[3:5] = inf_ref[j]
+        np.testing.assert_array_equal(kall[q], kp)
+        alpha = float(np.arctan2(np.float64(do[rows[j], 8]), np.float64(do[rows[j], 9])))
+        pb = BS.Problem(shape, g["p2"], g["p3"], alpha, do[rows[j], 5:8].astype(np.float64), pbl[rows[j], 4:8].astype(np.float64),
+                        pbr[rows[j], 4:8].astype(np.float64), kp.astype(np.float64))
+        s = poses[q, [0, 1, 2, 6]]
+        assert np.abs(pb.gradient(s)).max() < 1e-5, (q, pb.gradient(s))       # fp32-rounded end point of an fp64 solve
+        assert poses[q, 2] <= 100
+    assert ns >= n // 2
+    # rectification with synthetic aligned disparities
+    succ = torch.ones(R, device="cuda")
+    dis = torch.zeros(R, device="cuda")
+    dis[:ns] = c(np.array([g["disparity"][pos[int(r)]] for r in src], np.float32))
+    final = G.box_rectify(boxes_all, kpts_all, poses_all, succ, dis, nd, shape[:2], g["p2"], g["p3"]).cpu().numpy()
+    for q in range(ns):
+        j = pos[int(src[q])]
+        assert final[q, 0] == 1
+        f = g["p2"][0, 0]
+        z = f * ((g["p2"][0, 3] - g["p3"][0, 3]) / f) / float(np.float32(g["disparity"][j]))
+        assert abs(final[q, 8] - z) < 1e-9 * z
+        pr = BS.Problem(shape, g["p2"], g["p3"], float(poses_all[q, 7]), poses[q, 3:6], boxes_all[q, :4].cpu().numpy().astype(np.float64),
+                        None, kall[q].astype(np.float64), z_fixed=z)
+        assert np.abs(pr.gradient(final[q, [6, 7, 12]])).max() < 1e-8
+    assert (final[ns:, 0] == 0).all()
+    lines = G.kitti_result_lines(torch.from_numpy(final), float(g["t_cam2_cam0_x"]))
+    assert len(lines) == ns and lines[0].startswith("Car -1 -1 ")
+
+
+def test_pipeline_with_device_solver_runs_sync_free():
+    """the whole test_net.py per-image path incl. the solver stage, captured into a CUDA graph (proves there is no
+    host synchronisation anywhere) and replayed: identical results"""
+    H, W = 192, 416
+    sd = make_state_dict(3)
+    dev = torch.device("cuda")
+    pipe = PL.StereoPipeline(sd, dev, scale=1.0)
+    left, right = synth_pair(H, W, seed=21, shift=6)
+    iml, imr = torch.from_numpy(left)[None].cuda(), torch.from_numpy(right)[None].cuda()
+    p2, p3 = DEMO_P2 / np.array([[3.], [3.], [1.]]), DEMO_P3 / np.array([[3.], [3.], [1.]])
+    own = G.WorkspaceOwner()
+    with G.workspace_owner(own):
+        eager = pipe.step_with_solver(iml, imr, p2, p3, (H, W))
+        torch.cuda.synchronize()
+        runner = E.GraphRunner(lambda a, b: pipe.step_with_solver(a, b, p2, p3, (H, W)), [iml, imr])
+    out = runner()
+    torch.cuda.synchronize()
+    for k in ("record", "n_solved", "poses_all", "status", "best_dis", "final"):
+        assert torch.equal(out[k], eager[k]), k
+    assert int(out["nkeep"][0]) >= int(out["n_solved"][0]) >= 0
