@@ -187,7 +187,7 @@ int sb_test_decode(const float* rois_left, const float* rois_right, const float*
                    float* pred_kpts, sb_stream_t stream);
 /* the same decode that also emits the per-image detection record which ranks all-gather (the result
  * packing of test_net.py:233-330): record[r] = [cls_prob nc | boxes_left 4nc | boxes_right 4nc | dim_orien 5nc |
- * kpts 5], row pitch record_ld >= 15*nc + 5 floats                                                           */
+ * kpts 5], row pitch record_ld >= 14*nc + 5 floats                                                           */
 int sb_test_decode_record(const float* rois_left, const float* rois_right, const float* cls_prob,
                           const float* bbox_pred, const float* dim_orien, const float* kpts_prob,
                           const float* left_prob, const float* right_prob, const float* im_info, int R,
@@ -238,7 +238,7 @@ int sb_box_rectify(const float* boxes_all, const float* kpts_all, const float* p
                    const double* p3, double* final_out, sb_stream_t stream);
 
 /* ------------------------------------------------- record all-gather over peer memory ----
- * The path's only exchange: every rank's fixed-size detection record ([300, 15nc+5] fp32, ~40 KB) to every rank of
+ * The path's only exchange: every rank's fixed-size detection record ([300, 14nc+5] fp32, ~40 KB) to every rank of
  * one NVSwitch box.  Each rank owns a mailbox (sb_peer_alloc), exports it with CUDA IPC (sb_ipc_export, 64-byte
  * handle exchanged by the host's control plane) and maps its peers' (sb_ipc_import).  sb_peer_put_record stores the
  * local record into every mailbox (posted 128-bit NVLink writes + system-scope release of a sequence flag);

@@ -919,7 +919,7 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
 // can this conv run through the flat kernel with the TMA epilogue?  (fp16 operands, 1x1, dense [M, Cout] rows)
 bool flat_eligible(const sb_conv_desc* d, bool patch) {
     static const bool on = getenv("SB_TC_FLAT") == nullptr || atoi(getenv("SB_TC_FLAT")) != 0;
-    if (!on || d->in_dtype != 1 || patch || d->up_src || d->out_mode != 0) return false;
+    if (!on || d->in_dtype != 1 || patch || d->up_src || d->out_mode != 0 || d->res_biased || d->in_biased) return false;
     if (d->out_h_stride != (long long)d->Wo * d->out_w_stride || d->out_n_stride != (long long)d->Ho * d->out_h_stride) return false;
     if (d->residual && !d->out) return false;
     if (d->out && (((reinterpret_cast<uintptr_t>(d->out) + 4ull * d->out_coff) & 15) || (d->out_w_stride & 3))) return false;

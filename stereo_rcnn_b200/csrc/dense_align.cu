@@ -432,7 +432,7 @@ dense_final_kernel(Consts k, const float* __restrict__ poses, int pose_ld, const
     }
 }
 
-constexpr int kMaxSlices = 8;
+constexpr int kMaxSlices = 16;
 
 struct DaLayout { size_t part0, part1, total; };
 DaLayout da_layout(int H, int W, int D) {
@@ -514,7 +514,7 @@ static int dense_align_impl(const float* im_left, const float* im_right, int H, 
         if (e != cudaSuccess) return (int)e;
         attr_done[sb_cur_device()] = true;
     }
-    int S = 296 / D;                  // two waves of 148 SMs worth of CTAs
+    int S = 592 / D;                  // ~4 CTAs per SM: the per-row phases are latency bound, more CTAs hide it
     S = S < 1 ? 1 : (S > kMaxSlices ? kMaxSlices : S);
     dense_stage_kernel<0><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
     SB_LAUNCHED();

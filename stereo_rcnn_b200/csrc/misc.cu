@@ -514,7 +514,7 @@ extern "C" int sb_test_decode_record(const float* rois_left, const float* rois_r
                                      float* dim_orien_out, float* pred_kpts, float* record, int record_ld,
                                      sb_stream_t stream) {
     if (R == 0) return SB_OK;
-    if (!cls_prob || !record || record_ld < 15 * n_classes + 5) return SB_EINVAL;
+    if (!cls_prob || !record || record_ld < 14 * n_classes + 5) return SB_EINVAL;
     test_decode_kernel<<<sb_div_up(R, 128), 128, 0, sb_cs(stream)>>>(rois_left, rois_right, bbox_pred, dim_orien,
                                                                      kpts_prob, left_prob, right_prob, im_info, R,
                                                                      n_classes, grid, pred_boxes_left,

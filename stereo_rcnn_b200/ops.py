@@ -449,7 +449,7 @@ def test_decode(rois_left, rois_right, bbox_pred, dim_orien, kpts_prob, left_pro
 
 def test_decode_record(rois_left, rois_right, cls_prob, bbox_pred, dim_orien, kpts_prob, left_prob, right_prob,
                        im_info, n_classes=2, grid=28, record=None):
-    """test_decode + the [R, 15nc+5] detection record of the image (what ranks all-gather), one launch"""
+    """test_decode + the [R, 14nc+5] detection record of the image (what ranks all-gather), one launch"""
     L = _l.load()
     R = rois_left.shape[0]
     dev = rois_left.device
@@ -458,7 +458,7 @@ def test_decode_record(rois_left, rois_right, cls_prob, bbox_pred, dim_orien, kp
     do = torch.empty(R, 5 * n_classes, dtype=torch.float32, device=dev)
     pk = torch.empty(R, 5, dtype=torch.float32, device=dev)
     if record is None:
-        record = torch.empty(R, 15 * n_classes + 5, dtype=torch.float32, device=dev)
+        record = torch.empty(R, 14 * n_classes + 5, dtype=torch.float32, device=dev)
     check(L.sb_test_decode_record(ptr(_f32c(rois_left)), ptr(_f32c(rois_right)), ptr(_f32c(cls_prob)),
                                   ptr(_f32c(bbox_pred)), ptr(_f32c(dim_orien)), ptr(_f32c(kpts_prob)),
                                   ptr(_f32c(left_prob)), ptr(_f32c(right_prob)), ptr(_f32c(im_info)), R, n_classes,

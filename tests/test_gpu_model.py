@@ -294,7 +294,7 @@ def test_forward_small_vs_oracle_and_reference_golden(golden_dir):
     b = {tuple(np.round(x, 1)) for x in o["rois_left"][0].numpy()}
     frac = len(a & b) / float(len(b))
     print("end-to-end proposal set overlap: %.3f" % frac)
-    assert frac >= (0.98 if impl == "simt" else 0.5)
+    assert frac >= (0.98 if impl == "simt" else 0.80)      # measured 0.867 ... 0.873 (tf32 / fp16) on B200
 
 
 
