@@ -164,6 +164,10 @@ int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[
 int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream);
 /* fp16 variant: rows of 192 __half (147 taps zero padded to three 64-wide K-steps of kind::f16) */
 int sb_stem_im2col16(const float* im_nchw, int N, int H, int W, void* out_half, sb_stream_t stream);
+/* the stem on the tensor cores with the patch gather INSIDE the GEMM kernel (round 2: no patch matrix in memory):
+ * wgt16 = __half [64][192] ((ci, r, s) taps zero padded from 147), out16 = __half NHWC [N,Ho,Wo,64], BN + ReLU fused */
+int sb_stem_conv_tc(const float* im_nchw, int N, int H, int W, const void* wgt16, const float* scale,
+                    const float* shift, void* out16, sb_stream_t stream);
 /* MaxPool2d(3, stride 2, pad 0, ceil_mode) NHWC (resnet.py:113) */
 int sb_maxpool3x3s2_ceil(const float* in, int N, int H, int W, int C, float* out, sb_stream_t stream);
 int sb_maxpool3x3s2_ceil16(const void* in_half, int N, int H, int W, int C, void* out_half, sb_stream_t stream);

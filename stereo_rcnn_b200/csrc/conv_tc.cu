@@ -547,12 +547,15 @@ struct FlatParams {
     int num_m_tiles, num_n_tiles, num_k_blocks;
     int relu, has16, pdl_late;
     unsigned long long* trace;
+    // STEM variant: the A operand is gathered from the NCHW fp32 image (7x7 / stride 2 / pad 3 patches), no im2col
+    const float* stem_im;
+    int sH, sW, sHo, sWo;
 };
 
 constexpr int flat_epi_warp_bytes(bool res, bool f32) { return f32 ? ((res ? 3 : 2) * 4096 + 4096) : 4096; }
 
-template <int BLOCK_N, int kStages, bool HAS_RES, bool F32>
-__global__ void __launch_bounds__(320, 1)
+template <int BLOCK_N, int kStages, bool HAS_RES, bool F32, bool STEM = false>
+__global__ void __launch_bounds__(STEM ? 448 : 320, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_o32,
                     const __grid_constant__ CUtensorMap map_o16, const FlatParams p) {
@@ -591,7 +594,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1) {
         if (elect_one()) {
-            for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+            // STEM: a stage is full when the weight tile has landed (1 expect_tx arrival) and the 128 gather threads
+            // have written their patch rows
+            for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], STEM ? 129 : 1); mbar_init(&empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
             for (int i = 0; i < 24; ++i) mbar_init(&rfull[i], 1);
             fence_barrier_init();
@@ -621,8 +626,8 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kStageBytes;
-                    mbar_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(&map_a, &full[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
+                    mbar_expect_tx(&full[stage], STEM ? kBBytes : kStageBytes);
+                    if (!STEM) tma_load_2d(&map_a, &full[stage], sa, kb * BLOCK_K, mt * BLOCK_M);
                     tma_load_2d(&map_b, &full[stage], sa + kABytes, kb * BLOCK_K, nt * BLOCK_N);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -659,6 +664,63 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (tr && lane == 0) { tr[3] = gtimer(); tr[11] = clock64(); }
+    } else if (STEM && warp >= 10) {
+        // ===================== stem patch gather (warps 10..13) =====================
+        // The 7x7 / stride-2 / pad-3 stem convolution (resnet.py:111) as an implicit GEMM: thread gt builds row gt of
+        // the A tile -- the 147 taps (ci, r, s) of its output pixel, zero padded to 3 K-steps of 64 fp16 -- straight
+        // from the NCHW fp32 image into the 128-byte-swizzled stage (16-byte group j of row r at j ^ (r & 7)), so the
+        // 229 MB patch matrix of round 1 (sb_stem_im2col16) is never written or read.  Image reads hit L1 / L2: every
+        // input pixel is used by ~12 taps of neighbouring outputs.
+        const int gt = threadIdx.x - 320;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int H = p.sH, W = p.sW;
+        const long long HW = (long long)H * W;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / p.num_n_tiles;
+            const long long m = (long long)mt * BLOCK_M + gt;
+            const bool valid = m < p.M;
+            int n = 0, ho = 0, wo = 0;
+            if (valid) {
+                const int hw = p.sHo * p.sWo;
+                n = (int)(m / hw);
+                const int rem = (int)(m - (long long)n * hw);
+                ho = rem / p.sWo;
+                wo = rem - ho * p.sWo;
+            }
+            const int y0 = 2 * ho - 3, x0 = 2 * wo - 3;
+            const float* base = p.stem_im + (long long)n * 3 * HW + (long long)y0 * W + x0;
+            const bool interior = valid && y0 >= 0 && y0 + 6 < H && x0 >= 0 && x0 + 6 < W;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                const uint32_t row = smem_u32(smem + stage * kStageBytes) + gt * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t h[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        float v[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = kb * 64 + 8 * j + 2 * e2 + e;       // compile-time after unrolling
+                            v[e] = 0.f;
+                            if (k < 147) {
+                                const int ci = k / 49, r = (k % 49) / 7, sx = k % 7;
+                                const bool ok = interior || (valid && y0 + r >= 0 && y0 + r < H && x0 + sx >= 0 && x0 + sx < W);
+                                if (ok) v[e] = __ldg(base + ci * HW + r * W + sx);
+                            }
+                        }
+                        __half2 pk = __floats2half2_rn(v[0], v[1]);
+                        h[e2] = *reinterpret_cast<uint32_t*>(&pk);
+                    }
+                    sts128u(row + ((uint32_t)(j ^ (gt & 7)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+                }
+                fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&full[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;            // TMEM lane quarter this warp may touch
@@ -881,7 +943,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
 }
 
 
-template <int BN, int ST, bool RES, bool F32>
+template <int BN, int ST, bool RES, bool F32, bool STEM = false>
 int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo32,
                 const CUtensorMap& mo16, const FlatParams& p, int max_ctas, cudaStream_t st) {
     constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 8 * (size_t)flat_epi_warp_bytes(RES, F32) +
@@ -890,7 +952,7 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     static bool attr_done[kSbMaxDevices] = {false};
     bool& attr = attr_done[sb_cur_device()];
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_flat_kernel<BN, ST, RES, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_flat_kernel<BN, ST, RES, F32, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
@@ -901,7 +963,7 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(320);
+    cfg.blockDim = dim3(STEM ? 448 : 320);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
@@ -909,7 +971,7 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_flat_kernel<BN, ST, RES, F32>, ma, mb, mr, mo32, mo16, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_flat_kernel<BN, ST, RES, F32, STEM>, ma, mb, mr, mo32, mo16, p);
     SB_LAUNCHED();
     if (le != cudaSuccess) return (int)le;
     SB_CHECK_LAUNCH();
@@ -1056,6 +1118,7 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         fp.M = p.M; fp.Cout = d->Cout; fp.res_ld = d->res_ld;
         fp.num_m_tiles = p.num_m_tiles; fp.num_n_tiles = p.num_n_tiles; fp.num_k_blocks = p.num_k_blocks;
         fp.relu = d->relu; fp.has16 = d->out16 ? 1 : 0; fp.pdl_late = p.pdl_late; fp.trace = p.trace;
+        fp.stem_im = nullptr; fp.sH = fp.sW = fp.sHo = fp.sWo = 0;
         CUtensorMap mr = ma, mo32 = ma, mo16 = ma;      // unused maps still need a valid descriptor
         const cuuint64_t dims[2] = {(cuuint64_t)d->Cout, (cuuint64_t)p.M};
         const cuuint32_t box[2] = {32, 32};
@@ -1095,4 +1158,40 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         case 256: return launch<256, 4, 8>(ma, mb, p, st);
         default: return launch<128, 6, 8>(ma, mb, p, st);
     }
+}
+
+// The stem (resnet.py:111-112: Conv2d(3, 64, 7, stride 2, pad 3) + frozen BN + ReLU) as an implicit GEMM on the tensor
+// cores, patches gathered inside the kernel (conv_tc_flat_kernel<.., STEM>): image NCHW fp32 [N,3,H,W], weights fp16
+// [64][192] in (ci, r, s) order zero padded from 147, out NHWC fp16 [N,Ho,Wo,64].
+extern "C" int sb_stem_conv_tc(const float* im_nchw, int N, int H, int W, const void* wgt16, const float* scale,
+                               const float* shift, void* out16, sb_stream_t stream) {
+    if (!im_nchw || !wgt16 || !out16 || N < 1 || H < 7 || W < 7) return SB_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(wgt16) & 15) || (reinterpret_cast<uintptr_t>(out16) & 15) ||
+        (reinterpret_cast<uintptr_t>(scale) & 15) || (reinterpret_cast<uintptr_t>(shift) & 15))
+        return SB_EINVAL;
+    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    FlatParams fp;
+    fp.scale = scale; fp.shift = shift; fp.residual = nullptr;
+    fp.M = (long long)N * Ho * Wo; fp.Cout = 64; fp.res_ld = 0;
+    if (fp.M >= 0x7fffffffLL) return SB_EINVAL;
+    fp.num_m_tiles = (int)((fp.M + BLOCK_M - 1) / BLOCK_M); fp.num_n_tiles = 1; fp.num_k_blocks = 3;
+    fp.relu = 1; fp.has16 = 1;
+    static const bool pdl_late = getenv("SB_PDL_LATE") == nullptr || atoi(getenv("SB_PDL_LATE")) != 0;
+    fp.pdl_late = pdl_late ? 1 : 0;
+    fp.trace = nullptr;
+    fp.stem_im = im_nchw; fp.sH = H; fp.sW = W; fp.sHo = Ho; fp.sWo = Wo;
+    CUtensorMap mb, mo16;
+    {
+        cuuint64_t dims[2] = {192, 64};
+        cuuint64_t strides[1] = {192 * 2};
+        cuuint32_t box[2] = {64, 64};
+        if (!make_map(&mb, wgt16, 2, dims, strides, box, true)) return SB_EINVAL;
+    }
+    {
+        const cuuint64_t dims[2] = {64, (cuuint64_t)fp.M};
+        const cuuint64_t str[1] = {64 * 2};
+        const cuuint32_t box[2] = {32, 32};
+        if (!make_map(&mo16, out16, 2, dims, str, box, true, CU_TENSOR_MAP_SWIZZLE_64B)) return SB_EINVAL;
+    }
+    return launch_flat<64, 8, false, false, true>(mb, mb, mb, mb, mo16, fp, 0, sb_cs(stream));
 }

@@ -50,6 +50,7 @@ class StereoRCNNEngine(object):
         self.precision = "fp32-simt" if conv_impl == "simt" else precision
         self.keep32 = False
         self.chain_ctas = int(os.environ.get("SB_CHAIN_CTAS", "0"))
+        self.stem_fused = os.environ.get("SB_STEM_FUSED", "0") != "0"
         self.rpn_streams = os.environ.get("SB_RPN_STREAMS", "1") != "0"
         self.head_streams = os.environ.get("SB_HEAD_STREAMS", "1") != "0"
         # lr_streams: run layers 3-4 of the left and the right image as two concurrent chains (lowest latency of a
@@ -216,7 +217,12 @@ class StereoRCNNEngine(object):
         """fp16-operand trunk: every conv input is an fp16 tensor (half the HBM bytes, kind::f16 = 2x the TF32
         MMA rate, same 11-bit significand); fp32 copies exist only where a non-conv consumer needs them
         (residual adds, FPN upsample source, RoIAlign, the user-visible P levels)."""
-        c0 = self._conv(ops.stem_im2col16(im_nchw), self.p["stem_gemm16"], relu=True, tag="stem", f32=False, f16=True)
+        if self.stem_fused:     # patches gathered inside the GEMM kernel: no 229 MB patch matrix
+            pc = self.p["stem_gemm16"]
+            c0 = ops.stem_conv_tc(im_nchw, pc.w16.view(64, 192), pc.scale, pc.shift)
+            self.impl_used["stem"] = "tc16-fused"
+        else:
+            c0 = self._conv(ops.stem_im2col16(im_nchw), self.p["stem_gemm16"], relu=True, tag="stem", f32=False, f16=True)
         c1 = ops.maxpool3x3s2_ceil(c0)
         feats = {"c1": c1.float() if self.keep32 else None, "c1_16": c1}
         x32, x16 = None, c1

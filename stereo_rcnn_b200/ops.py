@@ -379,6 +379,18 @@ def stem_im2col16(im_nchw):
     return out
 
 
+def stem_conv_tc(im_nchw, w16, scale, shift):
+    """stem conv7x7/2 + frozen BN + ReLU as an implicit tensor-core GEMM (patch gather inside the kernel)
+    -> fp16 NHWC [N, Ho, Wo, 64]; w16: fp16 [64,192] ((ci, r, s) taps zero padded from 147)"""
+    L = _l.load()
+    N, _, H, W = im_nchw.shape
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = torch.empty(N, Ho, Wo, 64, dtype=torch.float16, device=im_nchw.device)
+    check(L.sb_stem_conv_tc(ptr(_f32c(im_nchw)), N, H, W, ptr(w16), ptr(scale), ptr(shift), ptr(out), stream_ptr()),
+          "sb_stem_conv_tc")
+    return out
+
+
 def maxpool3x3s2_ceil(x):
     L = _l.load()
     N, H, W, C = x.shape

@@ -5,6 +5,8 @@ mkdir -p $out
 export PYTHONUNBUFFERED=1
 echo "== full gpu suite (flat kernel on = default)"
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -s > $out/pytest_all.log 2>&1; echo "rc=$?"; tail -12 $out/pytest_all.log
+echo "== stem fused into the GEMM producer (opt-in until verified)"
+SB_STEM_FUSED=1 timeout 400 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout 150 -s -k "forward_small_fp16 or schedules_agree" > $out/pytest_stem.log 2>&1; echo "rc=$?"; tail -4 $out/pytest_stem.log
 echo "== bench (default)"
 timeout 500 python bench.py > $out/bench_default.json 2> $out/bench_default.err; echo "rc=$?"; tail -c 300 $out/bench_default.err
 echo "== A/B"
