@@ -5,7 +5,8 @@
 // loop over RoIs with ~150 tiny kernels and host scalar reads each, builds a 38 MB uv grid,
 // then ~10 full passes over [50 x D x P x 3] intermediates per stage (3.7 GB each at D=2048).
 //
-// Here (round 2): the 2x-upsampled pair is never materialised (round 1 wrote 2 x 76 MB of it per call).
+// Here (round 2), for up to kStripMaxD = 48 RoIs (what a KITTI frame has): the 2x-upsampled pair is NOT materialised
+// (round 1 wrote 2 x 76 MB of it per call); beyond that -- the D = 128 ... 2048 sweep -- it is, see further down.
 //   K1/K2 dense_stage_kernel<0|1>: grid (RoI, row slice).  Thread 0 builds the 3D box (corners, the three visible
 //      planes by the nearest-vertex rule).  The CTA then walks its lattice rows; per row
 //        (a) one thread per lattice pixel runs the ray / plane / in-box test and samples the LEFT image -- each tap
@@ -21,7 +22,7 @@
 //      coarse argmin from the partial rows (fixed slice order).
 //   K3 dense_final_kernel: per-RoI argmins, outputs, and the reference's "no valid pixel anywhere ->
 //      return dis_init" early-out.
-// Only the source pair (28.6 MB, L2-resident), a few KB of partial sums and D x 2 outputs touch HBM.
+// Strip path: only the source pair (28.6 MB, L2-resident), a few KB of partial sums and D x 2 outputs touch HBM.
 //
 // Arithmetic mirrors oracle/csrc/oracle_ops.c (which is pinned to the reference's Python):
 // every fp32 step is an explicit _rn intrinsic in the reference's evaluation order.
@@ -333,6 +334,127 @@ __device__ __forceinline__ void stage_costs(const RoiCtx& g, const Consts& k, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Many-RoI path (D > kStripMaxD): with hundreds of RoIs per image the 2x-upsampled pair is worth materialising
+// once (59 us, 2 x 76 MB -- amortised over the RoIs: 3 % of the call at D = 2048) so that every tap is one 128-bit
+// load and each thread keeps all hypotheses of its pixels in registers.  Measured (tests/tools/dense_align_sweep.py):
+// 2.1 ms at D = 2048 against 5.3 ms for the strip kernel, which is built for the latency case (D <= 48: equal speed,
+// no 152 MB of traffic per call).
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const float* __restrict__ im0, const float* __restrict__ im1, int H, int W,
+                  float4* __restrict__ up0, float4* __restrict__ up1) {
+    const float* __restrict__ src = blockIdx.z ? im1 : im0;
+    float4* __restrict__ dst = blockIdx.z ? up1 : up0;
+    const int OH = 2 * H, OW = 2 * W;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= OW) return;
+    const float rh = (OH > 1) ? __fdiv_rn((float)(H - 1), (float)(OH - 1)) : 0.f;
+    const float rw = (OW > 1) ? __fdiv_rn((float)(W - 1), (float)(OW - 1)) : 0.f;
+    const float sy = __fmul_rn(rh, (float)y);
+    const int y1 = (int)sy;
+    const int yp = (y1 < H - 1) ? 1 : 0;
+    const float ly1 = __fsub_rn(sy, (float)y1), ly0 = __fsub_rn(1.f, ly1);
+    const float sx = __fmul_rn(rw, (float)x);
+    const int x1 = (int)sx;
+    const int xp = (x1 < W - 1) ? 1 : 0;
+    const float lx1 = __fsub_rn(sx, (float)x1), lx0 = __fsub_rn(1.f, lx1);
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* r0 = src + ((size_t)c * H + y1) * W;
+        const float* r1 = r0 + (size_t)yp * W;
+        float top = __fadd_rn(__fmul_rn(lx0, __ldg(r0 + x1)), __fmul_rn(lx1, __ldg(r0 + x1 + xp)));
+        float bot = __fadd_rn(__fmul_rn(lx0, __ldg(r1 + x1)), __fmul_rn(lx1, __ldg(r1 + x1 + xp)));
+        o[c] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    }
+    dst[(size_t)y * OW + x] = make_float4(o[0], o[1], o[2], 0.f);
+}
+
+
+// F.grid_sample(bilinear, border, align_corners=True) on the interleaved image
+__device__ __forceinline__ float3 grid_sample(const float4* __restrict__ im, int H, int W, float gx, float gy) {
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(H - 1));
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float x1 = __fadd_rn(x0, 1.f), y1 = __fadd_rn(y0, 1.f);
+    const float wx1 = __fsub_rn(ix, x0), wx0 = __fsub_rn(x1, ix);
+    const float wy1 = __fsub_rn(iy, y0), wy0 = __fsub_rn(y1, iy);
+    const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(wx1, wy0);
+    const float sw = __fmul_rn(wx0, wy1), se = __fmul_rn(wx1, wy1);
+    const int xi0 = (int)x0, yi0 = (int)y0;
+    const bool okx = xi0 + 1 <= W - 1, oky = yi0 + 1 <= H - 1;
+    const float4* p = im + (size_t)yi0 * W + xi0;
+    const float4 a = __ldg(p);
+    float3 v = make_float3(__fmul_rn(a.x, nw), __fmul_rn(a.y, nw), __fmul_rn(a.z, nw));
+    if (okx) {
+        const float4 b = __ldg(p + 1);
+        v.x = __fadd_rn(v.x, __fmul_rn(b.x, ne)); v.y = __fadd_rn(v.y, __fmul_rn(b.y, ne)); v.z = __fadd_rn(v.z, __fmul_rn(b.z, ne));
+    }
+    if (oky && wy1 != 0.f) {   // a zero-weight row adds +-0 : skipped loads do not change the sum
+        const float4 c = __ldg(p + W);
+        v.x = __fadd_rn(v.x, __fmul_rn(c.x, sw)); v.y = __fadd_rn(v.y, __fmul_rn(c.y, sw)); v.z = __fadd_rn(v.z, __fmul_rn(c.z, sw));
+        if (okx) {
+            const float4 d = __ldg(p + W + 1);
+            v.x = __fadd_rn(v.x, __fmul_rn(d.x, se)); v.y = __fadd_rn(v.y, __fmul_rn(d.y, se)); v.z = __fadd_rn(v.z, __fmul_rn(d.z, se));
+        }
+    }
+    return v;
+}
+
+// One stage of the depth search for one (RoI, lattice slice).  Every thread owns lattice pixels
+// q = slice*blockDim + tid (+ nslices*blockDim ...), keeps the SAD of all NH hypotheses in registers and the
+// CTA writes one partial row [NH costs, valid-pixel count] to `part`.
+
+template <int NH>
+__device__ __forceinline__ void stage_costs_up(const RoiCtx& g, const Consts& k, const float4* __restrict__ upL,
+                                            const float4* __restrict__ upR, const float* __restrict__ rdis,
+                                            float* __restrict__ red /*[8][NH+1]*/, int slice, int nslices,
+                                            float* __restrict__ part /*[NH+1] global*/) {
+    float acc[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) acc[h] = 0.f;
+    int cnt = 0;
+    const int total = g.nu * g.nv;
+    for (int q = slice * blockDim.x + threadIdx.x; q < total; q += nslices * blockDim.x) {
+        const int a = q / g.nu, b = q - a * g.nu;
+        const float u = (float)(g.u0 + b * g.su), v = (float)(g.v0 + a * g.sv);
+        float dz;
+        if (!ray_test(g, u, v, k, &dz)) continue;
+        ++cnt;
+        const float gy = __fdiv_rn(__fsub_rn(v, k.fh2), k.fh2);
+        const float3 L = grid_sample(upL, k.FH, k.FW, __fdiv_rn(__fsub_rn(u, k.fw2), k.fw2), gy);
+        const float zf = __fdiv_rn(dz, k.fb32);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const float d = __fdiv_rn(1.0f, __fadd_rn(zf, rdis[h]));
+            const float gx = __fdiv_rn(__fsub_rn(__fsub_rn(u, d), k.fw2), k.fw2);
+            const float3 R = grid_sample(upR, k.FH, k.FW, gx, gy);
+            acc[h] += fabsf(__fsub_rn(L.x, R.x)) + fabsf(__fsub_rn(L.y, R.y)) + fabsf(__fsub_rn(L.z, R.z));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        float s = warp_sum(acc[h]);
+        if (lane == 0) red[warp * (NH + 1) + h] = s;
+    }
+    {
+        float s = warp_sum((float)cnt);
+        if (lane == 0) red[warp * (NH + 1) + NH] = s;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    if (threadIdx.x <= NH) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += red[w * (NH + 1) + threadIdx.x];
+        part[threadIdx.x] = s;
+    }
+}
+
+
 // coarse depths (dense_align.py:280-285) and the argmin over the slices' partial sums (fixed slice order)
 __device__ __forceinline__ float coarse_depth(float z0, int h) {
     float d = __fadd_rn(__fsub_rn(z0, 12.5f), (float)(0.5 * h));
@@ -367,7 +489,8 @@ __device__ __forceinline__ int argmin_partials(const float* __restrict__ part, i
 // grid (D, S): S row slices per RoI so that a few dozen RoIs still fill the machine; dynamic smem = the strip
 template <int STAGE>
 __global__ void __launch_bounds__(256)
-dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR, Consts k,
+dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR, const float4* __restrict__ upL,
+                   const float4* __restrict__ upR, Consts k,
                    const float* __restrict__ box_left, const float* __restrict__ keypoints,
                    const float* __restrict__ poses, int box_ld, int pose_ld, float* __restrict__ part0 /*[D][S][51]*/,
                    float* __restrict__ part1 /*[D][S][21]*/, const int* __restrict__ n_dev) {
@@ -396,7 +519,8 @@ dense_stage_kernel(const float* __restrict__ imL, const float* __restrict__ imR,
     }
     __syncthreads();
     float* part = STAGE == 0 ? part0 + ((size_t)i * S + blockIdx.y) * 51 : part1 + ((size_t)i * S + blockIdx.y) * 21;
-    if (g.nu <= 64) stage_costs<NH, 64>(g, k, imL, imR, rdis, red, strip, blockIdx.y, S, part);
+    if (upL) stage_costs_up<NH>(g, k, upL, upR, rdis, red, blockIdx.y, S, part);          // materialised 2x pair
+    else if (g.nu <= 64) stage_costs<NH, 64>(g, k, imL, imR, rdis, red, strip, blockIdx.y, S, part);
     else stage_costs<NH, 128>(g, k, imL, imR, rdis, red, strip, blockIdx.y, S, part);
 }
 
@@ -434,13 +558,17 @@ dense_final_kernel(Consts k, const float* __restrict__ poses, int pose_ld, const
 
 constexpr int kMaxSlices = 16;
 
-struct DaLayout { size_t part0, part1, total; };
+constexpr int kStripMaxD = 48;       // up to this many RoIs: strip kernel; beyond: materialise the 2x pair once
+
+struct DaLayout { size_t upL, upR, part0, part1, total; };
 DaLayout da_layout(int H, int W, int D) {
-    (void)H; (void)W;
     DaLayout l;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
     const size_t d = (size_t)(D > 0 ? D : 1);
+    const size_t px = D > kStripMaxD ? (size_t)4 * H * W : 0;
+    l.upL = take(px * sizeof(float4));
+    l.upR = take(px * sizeof(float4));
     l.part0 = take(d * kMaxSlices * 51 * sizeof(float));
     l.part1 = take(d * kMaxSlices * 21 * sizeof(float));
     l.total = off;
@@ -487,6 +615,9 @@ static int dense_align_impl(const float* im_left, const float* im_right, int H, 
     cudaStream_t st = sb_cs(stream);
     float* part0 = (float*)(ws + l.part0);
     float* part1 = (float*)(ws + l.part1);
+    const bool materialise = D > kStripMaxD;
+    float4* upL = materialise ? (float4*)(ws + l.upL) : nullptr;
+    float4* upR = materialise ? (float4*)(ws + l.upR) : nullptr;
     // dense_align.py:255-266 (python floats = doubles, cast to fp32 where they meet a tensor)
     const double s2 = scale * 2.0;
     const double fd = calib4[0] * s2;
@@ -514,11 +645,17 @@ static int dense_align_impl(const float* im_left, const float* im_right, int H, 
         if (e != cudaSuccess) return (int)e;
         attr_done[sb_cur_device()] = true;
     }
-    int S = 592 / D;                  // ~4 CTAs per SM: the per-row phases are latency bound, more CTAs hide it
+    int S = (materialise ? 296 : 592) / D;     // strip kernel: ~4 CTAs per SM (its per-row phases are latency bound)
+    if (materialise) {
+        dim3 ugrid((k.FW + 255) / 256, k.FH, 2);
+        upsample2x_kernel<<<ugrid, 256, 0, st>>>(im_left, im_right, H, W, upL, upR);
+        SB_LAUNCHED();
+        SB_CHECK_LAUNCH();
+    }
     S = S < 1 ? 1 : (S > kMaxSlices ? kMaxSlices : S);
-    dense_stage_kernel<0><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
+    dense_stage_kernel<0><<<dim3(D, S), 256, materialise ? 0 : kStripBytes, st>>>(im_left, im_right, upL, upR, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
     SB_LAUNCHED();
-    dense_stage_kernel<1><<<dim3(D, S), 256, kStripBytes, st>>>(im_left, im_right, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
+    dense_stage_kernel<1><<<dim3(D, S), 256, materialise ? 0 : kStripBytes, st>>>(im_left, im_right, upL, upR, k, box_left, keypoints, poses, box_ld, pose_ld, part0, part1, n_dev);
     SB_LAUNCHED();
     dense_final_kernel<<<1, 256, 0, st>>>(k, poses, pose_ld, part0, part1, D, S, status, best_dis, n_dev);
     SB_LAUNCHED();
