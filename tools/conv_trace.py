@@ -29,13 +29,16 @@ def main():
     ap.add_argument("--out", default="gpurun_out/conv_trace.json")
     ap.add_argument("--segment", default="all")
     ap.add_argument("--max-launches", type=int, default=400)
+    ap.add_argument("--throughput", action="store_true", help="the throughput schedule: one batched chain, no stream forks")
     a = ap.parse_args()
     L = lib.load()
     H, W = 600, 1987
     left, right = synth_pair(H, W, 3, 48)
     im = torch.cat((torch.from_numpy(left)[None], torch.from_numpy(right)[None]), 0).cuda().contiguous()
     info = torch.tensor([[H, W, 1.6]], device="cuda")
-    eng = engine.StereoRCNNEngine(make_state_dict(3), "cuda")
+    eng = engine.StereoRCNNEngine(make_state_dict(3), "cuda", lr_streams=False if a.throughput else None)
+    if a.throughput:
+        eng.rpn_streams = eng.head_streams = False
 
     def fwd():
         feats = eng.trunk_fpn(im)
@@ -103,6 +106,24 @@ def main():
             x["id"], x["cin"], x["cout"], x["k"], x["M"], x["BN"], x["tiles"], x["ctas"], 1 if x["chain"] else 0,
             x["start_us"], x["first_work_us"], x["end_us"], x["span_us"], x["work_span_us"], x["wait_us"],
             x["fill_cyc"], x["mma_cyc"], x["epi1_cyc"], x["tail_cyc"], x["cta_cyc"], x["cta_cyc_max"], x["start_skew_us"]))
+
+
+    # SM time by class: sum over launches of (median CTA busy time x CTAs) / SMs, in us of a full GPU
+    cls = {}
+    clk_mhz = 1965.0
+    for x in rows:
+        key = ("%dx%d" % (x["k"], x["k"])) + ("+res" if x["res"] else "") + ("+up" if x["up"] else "") + \
+              (" flat" if x["small"] == 2 else "") + (" small-M" if x["M"] < 30000 else "")
+        c = cls.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0])
+        c[0] += 1
+        c[1] += x["cta_cyc"] * x["ctas"] / 148.0 / clk_mhz
+        c[2] += x["fill_cyc"] * x["ctas"] / 148.0 / clk_mhz
+        c[3] += x["mma_cyc"] * x["ctas"] / 148.0 / clk_mhz
+        c[4] += x["tail_cyc"] * x["ctas"] / 148.0 / clk_mhz
+    print("\nSM time by class (us of a full GPU at %.0f MHz): launches, total, of which fill / mma / tail" % clk_mhz)
+    for k_, c in sorted(cls.items(), key=lambda kv: -kv[1][1]):
+        print("%-28s %3d  %7.1f   %6.1f %7.1f %6.1f" % (k_, c[0], c[1], c[2], c[3], c[4]))
+    print("all convs: %.1f us" % sum(c[1] for c in cls.values()))
 
 
 if __name__ == "__main__":
