@@ -37,7 +37,7 @@ REC_COLS = 2 + 8 + 8 + 10 + 5        # scores, boxes L/R, dim_orien, kpts  (per 
 # algorithmic MACs per *pair* at test (SURVEY 8 header / BASELINE.md 3), for the roofline line
 TC_GMACS_PER_PAIR = 2 * (15.88 + 22.64 + 123.58 + 17.89 + 66.99 + 117.37) + 2.45 + 16.7 + 223.9
 # (the 2 x 2.81 GMAC stem GEMM is executed on the tensor cores too but not counted as algorithmic work here)
-CONV_DRAM_BYTES_PER_STEP = 5.654e9     # profiles/r01b_conv_dram.md (fp16-operand default, 213 conv launches)
+CONV_DRAM_BYTES_PER_STEP = 5.655e9     # profiles/r02c_conv_dram.md (fp16-operand default, 213 conv launches of one forward)
 
 
 def peaks():

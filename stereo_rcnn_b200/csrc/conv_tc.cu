@@ -982,7 +982,8 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
 bool flat_eligible(const sb_conv_desc* d, bool patch) {
     static const bool on = getenv("SB_TC_FLAT") == nullptr || atoi(getenv("SB_TC_FLAT")) != 0;
     if (!on || d->in_dtype != 1 || patch || d->up_src || d->out_mode != 0 || d->res_biased || d->in_biased) return false;
-    if (d->out_h_stride != (long long)d->Wo * d->out_w_stride || d->out_n_stride != (long long)d->Ho * d->out_h_stride) return false;
+    if (d->out_h_stride != (long long)d->Wo * d->out_w_stride) return false;
+    if (d->N > 1 && d->out_n_stride != (long long)d->Ho * d->out_h_stride) return false;      // rows must be equally spaced
     if (d->residual && !d->out) return false;
     if (d->out && (((reinterpret_cast<uintptr_t>(d->out) + 4ull * d->out_coff) & 15) || (d->out_w_stride & 3))) return false;
     if (d->out16 && (((reinterpret_cast<uintptr_t>(d->out16) + 2ull * d->out_coff) & 15) || (d->out_w_stride & 7))) return false;

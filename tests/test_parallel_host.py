@@ -27,6 +27,16 @@ def _worker(rank, world, port, q):
         parts = [torch.rand(P.REC_ROIS, w, generator=g) for w in (2, 8, 8, 10, 5)]
         rec = P.detection_record(*parts) + rank
         allrec = P.gather_records(rec, world, dist)
+        # the class bench.py uses (on CPU tensors its exchange is torch.distributed's collective, here over gloo):
+        # two slots, several steps, every rank must see every rank's record of the same (step, slot)
+        gat = P.RecordGather(world, rank, torch.device("cpu"), dist, n_slots=2)
+        assert gat.mode == "nccl" and "ncclAllGather" in gat.describe()
+        for step in range(3):
+            for slot in range(2):
+                mine = torch.full((P.REC_ROIS, P.REC_COLS), float(100 * step + 10 * slot + rank))
+                got = gat(slot, mine)
+                for r in range(world):
+                    assert torch.equal(got[r], torch.full((P.REC_ROIS, P.REC_COLS), float(100 * step + 10 * slot + r)))
         t = P.max_over_ranks(10.0 + rank, torch.device("cpu"), world, dist)
         q.put((rank, (b, e), allrec.shape, float(allrec[0].mean()), float(allrec[1].mean()), float(rec.mean()), t))
     finally:

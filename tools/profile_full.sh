@@ -20,9 +20,9 @@ cap nms_reduce nms_reduce_kernel 0
 cap stem_im2col stem_im2col16 0
 cap rank_sort rank_sort_kernel 0
 fi
-cap dense_stage0 "dense_stage_kernel<0>" 0
+cap dense_stage0 "dense_stage_kernel<.int.0>" 0
 cap class_nms class_nms_kernel 0
-cap conv_flat_res "conv_tc_flat_kernel<128, 3, true" 8
-cap conv_flat_f16 "conv_tc_flat_kernel<128, 6, false" 8
-cap conv_rpn_p2 "conv_tc_kernel<256, 4, false, false" 10
+cap conv_flat_res "conv_tc_flat_kernel<.int.128, .int.3" 8
+cap conv_flat_f16 "conv_tc_flat_kernel<.int.128, .int.6" 8
+cap conv_rpn_p2 "conv_tc_kernel<.int.256, .int.4, .bool.0, .bool.0" 10
 ls -la $out/full_${tag}_*.ncu-rep
