@@ -162,7 +162,8 @@ int sb_stem_conv(const float* im_nchw, int N, int H, int W, const float* wgt /*[
 /* stem as a tensor-core GEMM: patch matrix [N*Ho*Wo][160] (k = ci*49+r*7+s, zero padded from 147) that
  * sb_conv2d_tc then multiplies with the [64][160] stem weights (1x1 conv, Cin = 160)              */
 int sb_stem_im2col(const float* im_nchw, int N, int H, int W, float* out, sb_stream_t stream);
-/* fp16 variant: rows of 192 __half (147 taps zero padded to three 64-wide K-steps of kind::f16) */
+/* fp16 variant: rows of 152 __half (147 taps + 5 zeros; the GEMM multiplies them with [64][192] zero-padded weights,
+ * the tensor map zero-fills columns 152..191 of the third 64-wide K-step) */
 int sb_stem_im2col16(const float* im_nchw, int N, int H, int W, void* out_half, sb_stream_t stream);
 /* the stem on the tensor cores with the patch gather INSIDE the GEMM kernel (round 2: no patch matrix in memory):
  * wgt16 = __half [64][192] ((ci, r, s) taps zero padded from 147), out16 = __half NHWC [N,Ho,Wo,64], BN + ReLU fused */

@@ -277,6 +277,7 @@ stem_im2col_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, in
 // One CTA = 64 consecutive output pixels of one output row: the 7 x 3 input rows it needs (133 columns
 // each) are staged in shared memory with coalesced loads, then every thread emits 16-byte stores.
 constexpr int kI2cPix = 64;
+constexpr int kI2cGroups = 19;      // 16-byte groups per patch row (152 halves)
 __global__ void __launch_bounds__(256)
 stem_im2col16_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, int Wo, uint4* __restrict__ out) {
     constexpr int SW = 2 * kI2cPix + 5;            // staged columns
@@ -298,8 +299,10 @@ stem_im2col16_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, 
     }
     __syncthreads();
     const int npix = min(kI2cPix, Wo - wo0);
-    for (int e = threadIdx.x; e < npix * 24; e += 256) {
-        const int px = e / 24, g = e - px * 24;
+    // rows of 152 halves (19 x 16 B): the 147 taps + 5 zeros.  The GEMM's third K-step reads columns 128..191 through a
+    // tensor map whose inner extent is 152, so TMA zero-fills the rest and 40 of the 192 columns never exist in memory
+    for (int e = threadIdx.x; e < npix * kI2cGroups; e += 256) {
+        const int px = e / kI2cGroups, g = e - px * kI2cGroups;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -316,7 +319,7 @@ stem_im2col16_kernel(const float* __restrict__ im, int N, int H, int W, int Ho, 
         uint4 o;
         o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
         o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-        out[(((long long)n * Ho + ho) * Wo + wo0 + px) * 24 + g] = o;
+        out[(((long long)n * Ho + ho) * Wo + wo0 + px) * kI2cGroups + g] = o;
     }
 }
 

@@ -1100,7 +1100,9 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, TW, TH, 1};
         if (!make_map(&ma, d->in, 4, dims, strides, box, f16)) return SB_EINVAL;
     } else {
-        cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)p.M};
+        // a row may be SHORTER than Cin (in_ld < Cin: the stem's 152-wide patch rows under a 192-wide zero-padded weight):
+        // the map's inner extent is then the row length and TMA zero-fills the rest of the last K-step
+        cuuint64_t dims[2] = {(cuuint64_t)(d->in_ld < d->Cin ? d->in_ld : d->Cin), (cuuint64_t)p.M};
         cuuint64_t strides[1] = {(cuuint64_t)d->in_ld * esz};
         cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, BLOCK_M};
         if (!make_map(&ma, d->in, 2, dims, strides, box, f16)) return SB_EINVAL;

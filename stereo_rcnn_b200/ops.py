@@ -370,11 +370,12 @@ def stem_im2col(im_nchw):
 
 
 def stem_im2col16(im_nchw):
-    """-> fp16 [N, Ho, Wo, 192] patch matrix of the stem (147 taps zero-padded to 192)"""
+    """-> fp16 [N, Ho, Wo, 152] patch matrix of the stem (147 taps + 5 zeros; the GEMM's tensor map zero-fills up to
+    the 192 columns of its zero-padded weights)"""
     L = _l.load()
     N, _, H, W = im_nchw.shape
     Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-    out = torch.empty(N, Ho, Wo, 192, dtype=torch.float16, device=im_nchw.device)
+    out = torch.empty(N, Ho, Wo, 152, dtype=torch.float16, device=im_nchw.device)
     check(L.sb_stem_im2col16(ptr(_f32c(im_nchw)), N, H, W, ptr(out), stream_ptr()), "sb_stem_im2col16")
     return out
 
