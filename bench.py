@@ -90,6 +90,16 @@ def make_inputs(rank, j=0):
 
 
 SCALE32 = float(np.float32(SCALE))
+H_CAM, W_CAM = 375, 1242
+
+
+def make_frames(rank, j=0):
+    """a synthetic uint8 KITTI-shape camera pair [375,1242,3] BGR (what demo.py / test_net.py read from disk): the e2e
+    path ships these to the GPU and runs prep_im_for_blob (blob.py:44-64) there -> 2 x [3,600,1987] fp32"""
+    from stereo_rcnn_b200.synth import synth_pair
+    left, right = synth_pair(H_CAM, W_CAM, seed=3 + rank + 1000 * j, shift=30)
+    f = lambda a: np.ascontiguousarray(np.clip(np.rint(a.transpose(1, 2, 0) + 110.0), 0, 255).astype(np.uint8))
+    return f(left), f(right)
 
 
 def run_ours(args):
@@ -115,6 +125,9 @@ def run_ours(args):
     host_r = torch.from_numpy(np.stack([q[1] for q in pairs])).pin_memory()
     iml, imr = host_l.to(dev), host_r.to(dev)
     rois3d = [tuple(torch.from_numpy(x).to(dev) for x in q[2]) for q in pairs]
+    frames = [make_frames(rank, j) for j in range(MB)]
+    host_l8 = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()     # [MB,375,1242,3] uint8
+    host_r8 = torch.from_numpy(np.stack([f[1] for f in frames])).pin_memory()
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
     n_inflight = max(1, args.inflight)
     use_graph = os.environ.get("SB_GRAPH", "1") != "0"
@@ -145,6 +158,47 @@ def run_ours(args):
             for ev in self.freed:
                 ev.record()
             self.k, self.primed = 0, False
+            # e2e: uint8 camera frames -> staging (H2D) -> prep_im_for_blob on the device, straight into the graph's inputs
+            self.h_l8, self.h_r8 = host_l8[:mb], host_r8[:mb]
+            self.staging8 = [(torch.empty_like(self.h_l8, device=dev), torch.empty_like(self.h_r8, device=dev))
+                             for _ in self.staging]
+            self.ready8 = [torch.cuda.Event() for _ in self.staging]
+            self.freed8 = [torch.cuda.Event() for _ in self.staging]
+            for ev in self.freed8:
+                ev.record()
+            self.k8, self.primed8 = 0, False
+
+        def prefetch8(self, j):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(self.freed8[j])
+                self.staging8[j][0].copy_(self.h_l8, non_blocking=True)
+                self.staging8[j][1].copy_(self.h_r8, non_blocking=True)
+                self.ready8[j].record(copy_stream)
+
+        def step_e2e(self):
+            """the call a user of demo.py / test_net.py makes: uint8 camera frames on the host in, records out.  H2D
+            of the next frames (2 x 1.4 MB per pair, pinned host -> staging, copy stream) overlaps compute;
+            prep_im_for_blob runs on the device and writes the graph's fixed inputs; every step moves its own frames in
+            and its records out inside the timed region"""
+            nst = len(self.staging8)
+            j = self.k8 % nst
+            if not self.primed8:
+                self.prefetch8(j)
+                self.primed8 = True
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self.ready8[j])
+            for b_ in range(self.mb):
+                ops.prep_image(self.staging8[j][0][b_], SCALE, out=self.iml[b_])
+                ops.prep_image(self.staging8[j][1][b_], SCALE, out=self.imr[b_])
+            self.freed8[j].record(cur)
+            self.prefetch8((self.k8 + 1) % nst)
+            self.k8 += 1
+            rec, keep, nkeep, st, dis = self.run()
+            g = self.gather(self.index, rec.view(-1, REC_COLS))
+            self.host_rec.copy_(g, non_blocking=True)
+            for b_ in range(self.mb):
+                self.host_dis[b_].copy_(dis[b_], non_blocking=True)
+            return g, dis
 
         def prefetch(self, j):
             with torch.cuda.stream(copy_stream):
@@ -157,8 +211,9 @@ def run_ours(args):
             rec, keep, nkeep, st, dis = self.run()
             return self.gather(self.index, rec.view(-1, REC_COLS)), dis
 
-        def step_e2e(self):
-            """H2D of this slot's next pair(s) (pinned host -> staging, copy stream) overlaps compute; every step
+        def step_e2e_blob(self):
+            """round 1's end-to-end definition: PRE-RESIZED fp32 blobs on the host (28.6 MB per pair) -> H2D -> forward.
+            H2D of this slot's next pair(s) (pinned host -> staging, copy stream) overlaps compute; every step
             still moves its own 28.6 MB per pair in and its records out inside the timed region"""
             if use_graph:
                 nst = len(self.staging)
@@ -250,6 +305,7 @@ def run_ours(args):
     single = None
     if not pipelined:
         total_ms = timed(slots[0].step_resident, args.steps, W)
+        e2e_blob_ms = timed(slots[0].step_e2e_blob, args.steps, 1)
         e2e_ms = timed(slots[0].step_e2e, args.steps, 1)
     else:
         one_ms = timed(lat_slot.step_resident, args.steps, W)    # one pair in flight, reported beside the headline
@@ -258,7 +314,13 @@ def run_ours(args):
                   "schedule": "latency: left/right chains, RPN levels and box head forked onto a second stream",
                   "l2": "256 MB flush between timed iterations"}
         total_ms = timed_pipelined("step_resident", args.steps, W + n_inflight)
+        e2e_blob_ms = timed_pipelined("step_e2e_blob", args.steps, W + n_inflight)
         e2e_ms = timed_pipelined("step_e2e", args.steps, W + n_inflight)
+        # leave the synthetic fp32 pair in the slots' inputs again (the e2e legs overwrote them with the camera frames)
+        for sl in slots:
+            with torch.cuda.stream(sl.stream):
+                sl.load(iml[:sl.mb], imr[:sl.mb])
+                sl.run()
     # the exchange step alone (records already packed): device time of one gather per step, max over ranks
     gather_ms = None
     if world > 1:
@@ -281,6 +343,7 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * args.steps * MB / (total_ms / 1e3)
     e2e_value = world * args.steps * MB / (e2e_ms / 1e3)
+    e2e_blob_value = world * args.steps * MB / (e2e_blob_ms / 1e3)
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live with CUDA events ----
     roof = None
@@ -330,9 +393,16 @@ def run_ours(args):
                    "api": "stereo_rcnn_b200.pipeline.StereoPipeline.step via pipeline.GraphSlot",
                    "cuda_graph": use_graph, "parallelism": "dp%d (1 pair/rank)" % world,
                    "gather": gather.describe()},
+        # e2e: the repo's public call with HOST inputs as demo.py / test_net.py have them -- uint8 camera frames; the
+        # input pipeline (prep_im_for_blob) runs on the device.  e2e_fp32_blob: round 1's definition (pre-resized fp32
+        # blobs on the host, 10x the H2D bytes), kept for continuity.
         "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s",
-                "h2d_bytes_per_step": int(slots[0].h_l.numel() * 4 * 2),
-                "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},
+                "h2d_bytes_per_step": int(slots[0].h_l8.numel() * 2),
+                "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4),
+                "input": "uint8 %dx%dx3 frames (pinned host) -> H2D -> sb_prep_image on the device -> %dx%d fp32" % (H_CAM, W_CAM, H_NET, W_NET)},
+        "e2e_fp32_blob": {"value": round(e2e_blob_value, 3), "unit": "pairs/s",
+                          "h2d_bytes_per_step": int(slots[0].h_l.numel() * 4 * 2),
+                          "d2h_bytes_per_step": int(host_rec.numel() * 4 + host_dis.numel() * 4)},
         "gpu_launches": int(launches) * args.steps,
         "inflight_vs_single_max_rel_diff": [round(c, 9) for c in checks],
         "clocks": sampler.summary(), "roofline": roof,
