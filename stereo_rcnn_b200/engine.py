@@ -70,7 +70,10 @@ class StereoRCNNEngine(object):
         self.exact = conv_impl == "simt"
         PackedConv.round_weights = not self.exact
         PackedConv.make_half = self.half
-        sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
+        # Weights are folded and packed ON THE HOST (one-off, ~1 s) and reach the device by plain copies: no torch
+        # kernel runs on the GPU for it, so a profiler's launch window of a process that builds an engine shows this
+        # library's kernels, not ~950 elementwise launches of weight preparation.
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()
               if not k.endswith("num_batches_tracked")}
         self.p = {}
 
@@ -88,10 +91,10 @@ class StereoRCNNEngine(object):
         # stem: [64,3,7,7] -> [64][7][7][3]
         s, b = bn_fold("RCNN_layer0.1")
         self.stem = (_pack_conv(sd["RCNN_layer0.0.weight"]), s, b)
-        wst = torch.zeros(64, 160, 1, 1, device=self.device)          # stem as a GEMM over the padded patch matrix
+        wst = torch.zeros(64, 160, 1, 1)                              # stem as a GEMM over the padded patch matrix
         wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)      # (ci, r, s) order of sb_stem_im2col
         self.p["stem_gemm"] = PackedConv(wst, s, b, 0)
-        wst = torch.zeros(64, 192, 1, 1, device=self.device)          # fp16 variant: three 64-wide K-steps
+        wst = torch.zeros(64, 192, 1, 1)                              # fp16 variant: three 64-wide K-steps
         wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)
         self.p["stem_gemm16"] = PackedConv(wst, s, b, 0)
         for li, nb in enumerate(LAYERS):
@@ -107,8 +110,8 @@ class StereoRCNNEngine(object):
         for k in ("RCNN_smooth1", "RCNN_smooth2", "RCNN_smooth3", "RCNN_rpn.RPN_Conv"):
             conv_bias(k, 1)
         # RPN 1x1 heads fused: rows 0..5 cls logits, 6..23 box deltas, 24..31 zero padding
-        wh = torch.zeros(32, 1024, 1, 1, device=self.device)
-        bh = torch.zeros(32, device=self.device)
+        wh = torch.zeros(32, 1024, 1, 1)
+        bh = torch.zeros(32)
         wh[0:6] = sd["RCNN_rpn.RPN_cls_score.weight"]
         wh[6:24] = sd["RCNN_rpn.RPN_bbox_pred_left_right.weight"]
         bh[0:6] = sd["RCNN_rpn.RPN_cls_score.bias"]
@@ -129,6 +132,13 @@ class StereoRCNNEngine(object):
         self.fc = [sd[k].contiguous() for k in ("RCNN_cls_score.weight", "RCNN_cls_score.bias",
                                                 "RCNN_bbox_pred.weight", "RCNN_bbox_pred.bias",
                                                 "RCNN_dim_orien_pred.weight", "RCNN_dim_orien_pred.bias")]
+        # ---- host -> device (copies only)
+        mv = lambda t: None if t is None else t.contiguous().to(self.device)
+        for pc in list(self.p.values()) + [c for row in self.deconv for c in row]:
+            pc.w, pc.w16, pc.scale, pc.shift = mv(pc.w), mv(pc.w16), mv(pc.scale), mv(pc.shift)
+        self.stem = tuple(mv(t) for t in self.stem)
+        self.kpts_class = tuple(mv(t) for t in self.kpts_class)
+        self.fc = [mv(t) for t in self.fc]
 
     # ------------------------------------------------------------------ helpers
     def _conv(self, x, pc, relu=False, stride=1, residual=None, up_src=None, out=None, out_coff=0,
