@@ -1,12 +1,11 @@
 #!/bin/bash
-# One GPU-box session of round 2 (everything that needs a B200, batched into one gpurun call).
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-echo "== tests touched by the last changes"
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py -m gpu -q --timeout 300 -k "roi_align or forward_small_fp16 or stem" > $out/pytest_quick.log 2>&1; echo "rc=$?"; tail -3 $out/pytest_quick.log
-echo "== A/B"
+echo "== trace (stem 152)"
+timeout 300 python tools/conv_trace.py --throughput --out $out/conv_trace_tp2.json > $out/conv_trace_tp2.txt 2>&1; echo "rc=$?"; sed -n 1,6p $out/conv_trace_tp2.txt | cut -c1-170; tail -3 $out/conv_trace_tp2.txt
+echo "== bench default (with cpu baseline + parity) and noise A/B"
+timeout 500 python bench.py > $out/bench_default2.json 2> $out/bench_default2.err; echo "rc=$?"; tail -c 300 $out/bench_default2.err; cut -c1-200 $out/bench_default2.json
 timeout 900 tools/ab.sh tools/ab_variants.txt
-echo "== ncu full captures (conv flat, dense)"
-tools/profile_full.sh r02d conv-only
+tools/profile_mem.sh r02e
 nvidia-smi --query-gpu=name,memory.used --format=csv
