@@ -126,3 +126,18 @@ def test_product_solver_core_vs_reference(gold, host_lib):
     assert worse <= 0.1 * n, "LM ended in a worse basin than Newton-CG in %d of %d cases" % (worse, n)
     print("median |state - reference state| = %.3g, 90th pct %.3g (Newton-CG's own end points are unstable at this level)"
           % (np.median(dz), np.percentile(dz, 90)))
+
+
+def test_product_kitti_writer_text_vs_reference(gold):
+    """ops.kitti_result_lines (the product's host-side formatter of sb_box_rectify's output) reproduces the reference's
+    write_detection_results text (kitti_utils.py:440-460) character for character"""
+    import torch
+    from stereo_rcnn_b200 import ops
+    g = gold
+    a = g["kitti_args"]                       # pos(3), dim(3), orien, score
+    row = np.zeros((2, 13))
+    row[0, 0], row[0, 1] = 1.0, a[7]
+    row[0, 2:6] = g["box_left"][0]
+    row[0, 6:9], row[0, 9:12], row[0, 12] = a[0:3], a[3:6], a[6]
+    lines = ops.kitti_result_lines(torch.from_numpy(row), float(g["t_cam2_cam0_x"]))      # second row is invalid: skipped
+    assert lines == [str(g["kitti_line"])]
