@@ -6,8 +6,10 @@ out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-echo "== sanity: composed forward (covers the BN=32 flat instance of the RPN heads)"
+if [ "$N" -le 2 ]; then
+echo "== sanity: composed forward"
 timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout 150 -k "forward_small_fp16 or conv_tc_fp16" > $out/pytest_sanity_$N.log 2>&1; echo "rc=$?"; tail -3 $out/pytest_sanity_$N.log
+fi
 echo "== gather + shard equivalence tests ($N GPUs visible)"
 timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -q --timeout 500 -s -k "record_gather" > $out/pytest_multi_$N.log 2>&1; echo "rc=$?"; tail -6 $out/pytest_multi_$N.log
 echo "== bench N=$N, peer gather"
