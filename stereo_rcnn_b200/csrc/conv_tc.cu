@@ -62,11 +62,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 constexpr int kTraceWords = 16, kTraceCtas = 304;
 
-template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16, int EW>
+// CG2 (CTA pairs, `tcgen05.mma.cta_group::2`): the two CTAs of a 2-cluster compute two vertically adjacent 128-row
+// tiles against the SAME 256-wide weight tile; each CTA loads its own A tile and HALF of the weight tile (128 rows),
+// the leader (cluster rank 0) issues M = 256 MMAs that read both CTAs' shared memory and write each CTA's own TMEM.
+// Per SM and K-step that is 32 KB of operands for 512 MMA cycles (62 B/clk) instead of 48 KB (94 B/clk, above the
+// ~80 B/clk an SM ingests from L2): the 256-wide 3x3 convs become MMA-bound.  Barrier protocol on top of the
+// single-CTA one: the peer's warp 1 forwards "my stage is full" to the leader (remote mbarrier arrive), the leader's
+// commits are multicast to both CTAs' empty / tfull barriers, the peer's epilogue warps release the accumulator
+// stage on the leader's tempty barrier; cluster barriers fence set-up and tear-down.
+template <int BLOCK_N, int kStages, bool HAS_RES, bool HAS_UP, bool IN16, int EW, bool CG2 = false>
 __global__ void __launch_bounds__(64 + 32 * EW, EW == 4 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p) {
-    constexpr uint32_t kABytes = BLOCK_M * kRowBytes, kBBytes = BLOCK_N * kRowBytes;
+    static_assert(!CG2 || (BLOCK_N == 256 && IN16 && !HAS_RES && !HAS_UP && EW == 8), "CTA-pair variant");
+    constexpr uint32_t kABytes = BLOCK_M * kRowBytes, kBBytes = (CG2 ? BLOCK_N / 2 : BLOCK_N) * kRowBytes;
     constexpr int BLOCK_K = IN16 ? 64 : 32;     // elements per K-step
     constexpr uint32_t kStageBytes = kABytes + kBBytes;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -77,12 +86,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* empty = full + kStages;
     uint64_t* tfull = empty + kStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* pfull = tempty + 2;              // CG2, leader: "the peer's stage is full" (remote arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + (CG2 ? kStages : 0));
     float4* epi_stage = reinterpret_cast<float4*>(smem + kStages * kStageBytes + 256);   // [EW warps][32 rows][8 float4]
-    static_assert((2 * kStages + 4) * 8 + 16 <= 256, "barrier block");
+    static_assert(((CG2 ? 3 : 2) * kStages + 4) * 8 + 16 <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const sb_conv_desc& d = p.d;
+    const uint32_t crank = CG2 ? cluster_ctarank() : 0u;      // 0 = leader
     unsigned long long* tr = p.trace ? p.trace + (size_t)blockIdx.x * kTraceWords : nullptr;
     if (tr && threadIdx.x == 0) {
         unsigned smid;
@@ -97,16 +108,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 1) {
         if (elect_one()) {
             for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EW); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG2 ? 2 * EW : EW); }
+            if (CG2) for (int i = 0; i < kStages; ++i) mbar_init(&pfull[i], 1);
             fence_barrier_init();
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (CG2) {      // one warp of EACH CTA of the pair takes part in the pair-wide allocation
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all();     // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch,
@@ -116,15 +135,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tr && threadIdx.x == 0) { tr[1] = gtimer(); tr[9] = clock64(); }
 
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // CG2: a "tile" of the loops below is a PAIR of row tiles (2q, 2q+1) x one 256-wide column tile, one pair per
+    // cluster; this CTA owns row tile 2q + crank (past the end for an odd count: loads zero-fill, stores are masked)
+    const int num_tiles = CG2 ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles;
+    const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstep = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_tile = [&](int tile) { const int q = tile / p.num_n_tiles; return CG2 ? 2 * q + (int)crank : q; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+            for (int tile = tile0; tile < num_tiles; tile += tstep) {
+                const int mt = row_tile(tile), nt = tile % p.num_n_tiles;
                 int n_img = 0, h0 = 0, w0 = 0;
                 if (p.patch) {
                     const int tw = mt % p.tiles_w;
@@ -146,37 +170,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     } else {
                         tma_load_2d(&map_a, &full[stage], sa, c0, mt * BLOCK_M);
                     }
-                    tma_load_2d(&map_b, &full[stage], sb, tap * d.Cin + c0, nt * BLOCK_N);
+                    // CG2: this CTA's half (128 rows) of the pair's 256-row weight tile
+                    tma_load_2d(&map_b, &full[stage], sb, tap * d.Cin + c0, nt * BLOCK_N + (CG2 ? (int)crank * (BLOCK_N / 2) : 0));
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
+    } else if (warp == 1 && CG2 && crank != 0) {
+        // ===================== peer CTA: forward "stage full" to the leader =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                mbar_wait(&full[stage], phase);                       // my A tile and my half of the weights have landed
+                if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&pfull[stage]), 0));
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (tr && lane == 0) { tr[3] = gtimer(); tr[11] = clock64(); }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc(BLOCK_N, IN16);
+        // ===================== MMA issuer (CG2: leader CTA only) =====================
+        constexpr uint32_t idesc = CG2 ? make_idesc_2cta(BLOCK_N, IN16) : make_idesc(BLOCK_N, IN16);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
+            if (CG2) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);    // released by the epilogues of BOTH CTAs
+            else mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(&full[stage], phase);
+                if (CG2) mbar_wait_cluster(&pfull[stage], phase);
                 tc_fence_after();
-                if (tr && lane == 0 && kb == 0 && tile == (int)blockIdx.x) { tr[2] = gtimer(); tr[10] = clock64(); }
+                if (tr && lane == 0 && kb == 0 && tile == tile0) { tr[2] = gtimer(); tr[10] = clock64(); }
                 if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         // advance 32 bytes (8 tf32) inside the 128-byte swizzle row: +2 in 16-byte units
-                        if (IN16) umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        if (CG2) umma_f16_2cta(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        else if (IN16) umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                         else umma_tf32(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty[stage]);                       // frees the smem slot when the MMAs retire
-                    if (kb == p.num_k_blocks - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                    if (CG2) {
+                        umma_commit_2cta(&empty[stage]);                  // frees the slot in BOTH CTAs
+                        if (kb == p.num_k_blocks - 1) umma_commit_2cta(&tfull[acc]);
+                    } else {
+                        umma_commit(&empty[stage]);                       // frees the smem slot when the MMAs retire
+                        if (kb == p.num_k_blocks - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -261,8 +308,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         };
         if (HAS_RES && has_cols) prefetch_res_tile(blockIdx.x + gridDim.x);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+        for (int tile = tile0; tile < num_tiles; tile += tstep) {
+            const int mt = row_tile(tile), nt = tile % p.num_n_tiles;
             if (HAS_RES && has_cols) prefetch_res_tile(tile + 2 * gridDim.x);
             unsigned ooff[8];          // element offsets < 2^31 (checked on the host)
             unsigned vmask = 0;
@@ -279,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     ho = (t2 % p.tiles_h) * TH + row / TW;
                     wo = tw * TW + row % TW;
                     n_img = t2 / p.tiles_h;
-                    valid = ho < d.Ho && wo < d.Wo;
+                    valid = ho < d.Ho && wo < d.Wo && n_img < d.N;      // (n_img >= N: the pad tile of an odd CTA pair)
                 } else {
                     const long long m = (long long)mt * BLOCK_M + row;
                     valid = m < p.M;
@@ -509,18 +556,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-            if (tr && warp == 2 && lane == 0 && tile == (int)blockIdx.x) { tr[4] = gtimer(); tr[12] = clock64(); }
+            if (lane == 0) {
+                // CG2: the accumulator stage of the PAIR is free when the epilogue warps of both CTAs are done with it;
+                // the barrier the MMA warp waits on lives in the leader
+                if (CG2 && crank != 0) mbar_arrive_remote(mapa_rank(smem_u32(&tempty[acc]), 0));
+                else mbar_arrive(&tempty[acc]);
+            }
+            if (tr && warp == 2 && lane == 0 && tile == tile0) { tr[4] = gtimer(); tr[12] = clock64(); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all();      // neither CTA may retire (or free TMEM) while the other can still reach into it
+    else __syncthreads();
     if (tr && threadIdx.x == 0) { tr[5] = gtimer(); tr[13] = clock64(); }
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -885,6 +939,43 @@ int pick_block_n(int cout, long long m_tiles, int num_sms) {
     return c256 <= c128 ? 256 : 128;
 }
 
+// CTA-pair launch: clusters of 2, one pair per two SMs, 6 stages of 32 KB (A tile + half a weight tile)
+int launch_cg2(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    constexpr int ST = 6, BN = 256;
+    constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + (BN / 2) * kRowBytes) + 1024 + 256 + epi_smem(8);
+    static_assert(smem <= 227 * 1024, "smem budget");
+    auto kern = conv_tc_kernel<BN, ST, false, false, true, 8, true>;
+    static bool attr_done[kSbMaxDevices] = {false};
+    bool& attr = attr_done[sb_cur_device()];
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    int pairs = sb_num_sms() / 2;
+    if (p.d.max_ctas > 1 && p.d.max_ctas / 2 < pairs) pairs = p.d.max_ctas / 2;
+    if (pair_tiles < pairs) pairs = pair_tiles;
+    static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(64 + 32 * 8);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 2; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = use_pdl ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
+    SB_LAUNCHED();
+    if (le != cudaSuccess) return (int)le;
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
 template <int BN, int ST, bool RES, bool UP, bool IN16, int EW>
 int launch_t(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)ST * (BLOCK_M * kRowBytes + BN * kRowBytes) + 1024 + 256 + epi_smem(EW);
@@ -1084,12 +1175,16 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         flat = (BN == 32 && d->out && !d->out16 && !d->residual) || (BN == 64 && f16only) || BN == 128 || (BN == 256 && f16only);
     }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
+    // CTA pairs (cta_group::2) for the 256-wide 3x3 convs: opt-in until verified (SB_TC_CG2=1)
+    static const bool cg2_on = getenv("SB_TC_CG2") != nullptr && atoi(getenv("SB_TC_CG2")) != 0;
+    const bool cg2 = cg2_on && !flat && !small && f16 && p.patch && d->kh == 3 && !d->up_src && !d->residual && BN == 256 &&
+                     d->Cout % 256 == 0 && p.num_m_tiles >= 2;
     if (g_trace && g_trace_n < g_trace_cap) {
         const int id = g_trace_n++;
         p.trace = g_trace + (size_t)id * kTraceCtas * kTraceWords;
         int* v = g_trace_info[id].v;
         v[0] = d->Cin; v[1] = d->Cout; v[2] = d->kh; v[3] = (int)p.M; v[4] = BN; v[5] = p.num_m_tiles * p.num_n_tiles;
-        v[6] = p.num_k_blocks; v[7] = d->residual ? 1 : 0; v[8] = d->up_src ? 1 : 0; v[9] = small ? 1 : (flat ? 2 : 0);
+        v[6] = p.num_k_blocks; v[7] = d->residual ? 1 : 0; v[8] = d->up_src ? 1 : 0; v[9] = small ? 1 : (flat ? 2 : (cg2 ? 3 : 0));
         v[10] = d->max_ctas; v[11] = d->N;
     }
     CUtensorMap ma, mb;
@@ -1111,10 +1206,11 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         const cuuint64_t ktot = (cuuint64_t)d->kh * d->kw * d->Cin;
         cuuint64_t dims[2] = {ktot, (cuuint64_t)d->Cout};
         cuuint64_t strides[1] = {ktot * esz};
-        cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
+        cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(cg2 ? BN / 2 : BN)};     // cg2: each CTA loads half the tile
         if (!make_map(&mb, d->wgt, 2, dims, strides, box, f16)) return SB_EINVAL;
     }
     cudaStream_t st = sb_cs(stream);
+    if (cg2) return launch_cg2(ma, mb, p, st);
     if (flat) {
         FlatParams fp;
         fp.scale = d->scale; fp.shift = d->shift; fp.residual = d->residual;

@@ -125,6 +125,7 @@ TC_CASES = [
     (300, 25088, 1, 1, 2048, 1),
     (2, 1024, 38, 125, 256, 1),      # 75 m-tiles: the wave model picks BLOCK_N = 256
     (2, 256, 38, 125, 1024, 1),
+    (3, 64, 40, 80, 256, 3),         # 75 spatial tiles (odd): BLOCK_N = 256; with SB_TC_CG2=1 38 CTA pairs, one pad tile
 ]
 
 
