@@ -139,8 +139,10 @@ def run_ours(args):
     pipe_lat = pipeline.StereoPipeline(sd, dev, scale=SCALE)             # one pair at a time: lowest latency
     pipe = pipeline.StereoPipeline(sd, dev, throughput=True, scale=SCALE) if (n_inflight > 1 or MB > 1) else pipe_lat
     copy_stream = torch.cuda.Stream(device=dev)
+    # peer mode runs the exchange pipelined (lag 1): a step puts its record and collects the previous step's, so no
+    # rank waits for a slower peer's current step; the last step of every slot is drained inside the timed region
     gather = parallel.RecordGather(world, rank, dev, dist, n_slots=n_inflight + 1, mode=args.gather,
-                                   rec_shape=(MB * N_ROIS, REC_COLS))
+                                   rec_shape=(MB * N_ROIS, REC_COLS), lag=args.gather_lag)
 
     class Slot(pipeline.GraphSlot):
         """a GraphSlot plus the bench's host side: the pinned-host staging of the next H2D and the host landing
@@ -268,13 +270,14 @@ def run_ours(args):
             return g, dis
 
     # the latency slot always runs ONE pair at a time (batch 1, the reference's test configuration)
-    gather_lat = gather if MB == 1 else parallel.RecordGather(world, rank, dev, dist, n_slots=1, mode=args.gather)
+    gather_lat = gather if MB == 1 else parallel.RecordGather(world, rank, dev, dist, n_slots=1, mode=args.gather,
+                                                              lag=args.gather_lag)
     pipelined = n_inflight > 1 or MB > 1
     lat_slot = Slot(pipe_lat, False, n_inflight if (pipelined and MB == 1) else 0, gather_lat, 1)
     slots = [Slot(pipe, True, i, gather, MB) for i in range(n_inflight)] if pipelined else [lat_slot]
     host_rec, host_dis = slots[0].host_rec, slots[0].host_dis
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, drain=None):
         """one pair in flight: every step bracketed by its own events, L2 flushed (untimed) between steps"""
         for _ in range(warmup):
             fn()
@@ -287,6 +290,8 @@ def run_ours(args):
             ops.l2_flush(flush)          # untimed, between iterations
             s.record()
             fn()
+            if drain is not None:
+                drain()                  # pipelined exchange: the step is complete when its records have been collected
             e.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -317,6 +322,11 @@ def run_ours(args):
             sl.stream.wait_event(s)
         for k in range(steps):
             issue(k)
+        for sl in slots:                     # pipelined exchange: collect the last step's records of every slot
+            with torch.cuda.stream(sl.stream):
+                g_ = sl.gather.drain(sl.index)
+                if g_ is not None and method != "step_resident":
+                    sl.host_rec.copy_(g_, non_blocking=True)
         for sl in slots:
             main.wait_stream(sl.stream)
         main.wait_stream(copy_stream)
@@ -335,13 +345,14 @@ def run_ours(args):
     W = max(args.warmup, 3)
     single = None
     if not pipelined:
-        total_ms = timed(slots[0].step_resident, args.steps, W)
-        e2e_blob_ms = timed(slots[0].step_e2e_blob, args.steps, 1)
+        dr = lambda: slots[0].gather.drain(slots[0].index)
+        total_ms = timed(slots[0].step_resident, args.steps, W, dr)
+        e2e_blob_ms = timed(slots[0].step_e2e_blob, args.steps, 1, dr)
         if use_graph:
             slots[0].build_e2e_graph()
-        e2e_ms = timed(slots[0].step_e2e, args.steps, 1)
+        e2e_ms = timed(slots[0].step_e2e, args.steps, 1, dr)
     else:
-        one_ms = timed(lat_slot.step_resident, args.steps, W)    # one pair in flight, reported beside the headline
+        one_ms = timed(lat_slot.step_resident, args.steps, W, lambda: lat_slot.gather.drain(lat_slot.index))    # one pair in flight, reported beside the headline
         single = {"inflight": 1, "ms_per_step": round(one_ms / args.steps, 3),
                   "value": round(world * args.steps / (one_ms / 1e3), 3), "unit": "pairs/s",
                   "schedule": "latency: left/right chains, RPN levels and box head forked onto a second stream",
@@ -361,7 +372,7 @@ def run_ours(args):
     gather_ms = None
     if world > 1:
         rec0 = slots[0].outputs[0].view(-1, REC_COLS)
-        gather_ms = timed(lambda: gather(slots[0].index, rec0), args.steps, W) / args.steps
+        gather_ms = timed(lambda: gather(slots[0].index, rec0), args.steps, W, lambda: gather.drain(slots[0].index)) / args.steps
         gather.check()
     # every in-flight slot must have produced the result of the one-pair-at-a-time run on the same input: the
     # schedules differ only in tile widths / stream forks, proposals are index-exact and records agree to rounding
@@ -667,6 +678,8 @@ def main():
                     help="record exchange at N>1: own peer-memory kernels (default) or ncclAllGather")
     ap.add_argument("--microbatch", type=int, default=int(os.environ.get("SB_MICROBATCH", "1")),
                     help="pairs per step of one in-flight slot, batched through every launch (M-batching)")
+    ap.add_argument("--gather-lag", type=int, default=int(os.environ.get("SB_GATHER_LAG", "1")), choices=[0, 1],
+                    help="peer exchange: 1 = pipelined (a step collects the previous step's records), 0 = same step")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("SB_INFLIGHT", "3")),
                     help="independent pairs in flight per GPU (each batch-1, own stream + CUDA graph)")
     args = ap.parse_args()

@@ -260,7 +260,9 @@ int sb_ipc_import(const void* handle64, void** ptr);
 int sb_ipc_close(void* ptr);
 int sb_peer_put_record(const float* rec, void* const* mailboxes, int n_slots, int world, int rec_floats,
                        int rank, int slot, sb_stream_t stream);
-int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, float* gathered,
+/* lag = 0: collect the step just put; lag = 1: collect the PREVIOUS step of this slot (pipelined exchange: no rank
+ * waits for a slower peer's current step; the first call of a slot leaves `gathered` untouched) */
+int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, int lag, float* gathered,
                          int* err_flag, double timeout_s, sb_stream_t stream);
 
 #ifdef __cplusplus

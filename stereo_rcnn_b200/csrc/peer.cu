@@ -3,7 +3,7 @@
 //
 // Every rank owns one "mailbox" allocation (cudaMalloc, exported with CUDA IPC and mapped by every peer):
 //
-//   data  [n_slots][2 parities][world][rec_floats]   records as they arrive from each rank
+//   data  [n_slots][4 parities][world][rec_floats]   records as they arrive from each rank
 //   flags [n_slots][world]                           sequence number of the newest record of (slot, rank)
 //   seq   [n_slots]                                   this rank's own step counter per slot (device-resident, so
 //                                                     that put/wait can be captured into a CUDA graph and replayed)
@@ -13,14 +13,18 @@
 // wait : CTA q acquires flag (slot, q) of the LOCAL mailbox, then copies rank q's record out of the mailbox into
 //        the caller's gathered tensor.  The spin is bounded (%globaltimer) so that a lost peer cannot hang the GPU.
 //
-// Two parities per slot make the mailbox safe without an acknowledgement: a rank can only be two steps ahead of a
-// peer in the same slot after that peer has delivered the step in between, which it issues (stream order) after
-// the copy-out of the step before.  NCCL stays the control plane (rendezvous, handle exchange, barriers).
+// Four buffers ("parities", step & 3) per slot make the mailbox safe without an acknowledgement, also when the
+// consumer runs `lag` = 1 step behind the producers (put step s, then collect step s-1: no rank ever blocks on a
+// slower peer's CURRENT step, only on its previous one): a rank passes its wait for step t only after every peer has
+// put step t-1, which each issues (stream order) before copying out step t-2 -- so while a peer still reads t-2 the
+// fastest rank can have written at most t+1: four live records.  NCCL stays the control plane (rendezvous, handle
+// exchange, barriers).
 #include "common.cuh"
 
 namespace {
 
 constexpr int kMaxPeers = 16;
+constexpr int kParities = 4;
 
 struct PeerPtrs {
     float* p[kMaxPeers];
@@ -42,9 +46,9 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 
 struct Layout {
     int n_slots, world, rec_floats;     // rec_floats % 4 == 0
-    __host__ __device__ size_t data_floats() const { return (size_t)n_slots * 2 * world * rec_floats; }
+    __host__ __device__ size_t data_floats() const { return (size_t)n_slots * kParities * world * rec_floats; }
     __host__ __device__ size_t data_off(int slot, int par, int r) const {
-        return (((size_t)slot * 2 + par) * world + r) * rec_floats;
+        return (((size_t)slot * kParities + par) * world + r) * rec_floats;
     }
     __host__ __device__ size_t flag_off(int slot, int r) const { return (size_t)slot * world + r; }   // in u32 after data
     __host__ __device__ size_t seq_off(int slot) const { return (size_t)n_slots * world + slot; }
@@ -61,7 +65,7 @@ peer_put_kernel(const float* __restrict__ rec, PeerPtrs peers, Layout L, int ran
     }
     __syncthreads();
     const unsigned seq = s_seq;
-    const int par = (int)(seq & 1u);
+    const int par = (int)(seq % kParities);
     const int n4 = L.rec_floats / 4;
     const float4* src = reinterpret_cast<const float4*>(rec);
     for (int p = 0; p < L.world; ++p) {
@@ -77,14 +81,16 @@ peer_put_kernel(const float* __restrict__ rec, PeerPtrs peers, Layout L, int ran
 }
 
 __global__ void __launch_bounds__(256)
-peer_wait_kernel(float* __restrict__ mailbox, Layout L, int slot, float* __restrict__ out, int* __restrict__ err,
+peer_wait_kernel(float* __restrict__ mailbox, Layout L, int slot, int lag, float* __restrict__ out, int* __restrict__ err,
                  unsigned long long timeout_ns) {
     const int q = blockIdx.x;
     unsigned* ctl = reinterpret_cast<unsigned*>(mailbox + L.data_floats());
     __shared__ unsigned s_seq;
     __shared__ int s_ok;
+    const unsigned cur = ctl[L.seq_off(slot)];          // written by this rank's put (stream order)
+    if ((int)cur - lag < 1) return;                     // nothing that old has been put yet (first `lag` calls): CTA-uniform
     if (threadIdx.x == 0) {
-        const unsigned seq = ctl[L.seq_off(slot)];      // written by this rank's put (stream order)
+        const unsigned seq = cur - (unsigned)lag;
         const unsigned long long t0 = gtime_ns();
         int ok = 1;
         while ((int)(ld_acquire_sys(ctl + L.flag_off(slot, q)) - seq) < 0) {
@@ -97,7 +103,7 @@ peer_wait_kernel(float* __restrict__ mailbox, Layout L, int slot, float* __restr
     }
     __syncthreads();
     if (!s_ok) return;
-    const int par = (int)(s_seq & 1u);
+    const int par = (int)(s_seq % kParities);
     const float4* src = reinterpret_cast<const float4*>(mailbox + L.data_off(slot, par, q));
     float4* dst = reinterpret_cast<float4*>(out + (size_t)q * L.rec_floats);
     for (int i = threadIdx.x; i < L.rec_floats / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
@@ -155,13 +161,13 @@ extern "C" int sb_peer_put_record(const float* rec, void* const* mailboxes, int 
     return SB_OK;
 }
 
-extern "C" int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, float* gathered,
-                                    int* err_flag, double timeout_s, sb_stream_t stream) {
-    if (!mailbox || !gathered || !err_flag || world < 1 || world > kMaxPeers || slot < 0 || slot >= n_slots ||
+extern "C" int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, int lag,
+                                    float* gathered, int* err_flag, double timeout_s, sb_stream_t stream) {
+    if (!mailbox || !gathered || !err_flag || world < 1 || world > kMaxPeers || slot < 0 || slot >= n_slots || lag < 0 || lag > 1 ||
         rec_floats < 4 || (rec_floats & 3) || (reinterpret_cast<uintptr_t>(gathered) & 15))
         return SB_EINVAL;
     peer_wait_kernel<<<world, 256, 0, sb_cs(stream)>>>(static_cast<float*>(mailbox), make_layout(n_slots, world, rec_floats),
-                                                       slot, gathered, err_flag,
+                                                       slot, lag, gathered, err_flag,
                                                        (unsigned long long)(timeout_s * 1e9));
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();

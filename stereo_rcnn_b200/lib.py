@@ -95,7 +95,7 @@ _SIGS = {
     "sb_ipc_import": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "sb_ipc_close": (c_int, [c_void_p]),
     "sb_peer_put_record": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "sb_peer_wait_records": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p]),
+    "sb_peer_wait_records": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -54,13 +54,17 @@ class RecordGather(object):
     """
 
     def __init__(self, world, rank, device, dist=None, n_slots=1, mode=None, rec_shape=(REC_ROIS, REC_COLS),
-                 timeout_s=20.0):
+                 timeout_s=20.0, lag=0):
+        """lag = 1 (peer mode only): pipelined exchange -- a call puts this step's record and returns the gathered
+        records of the slot's PREVIOUS step, so that no rank ever waits for a slower peer's current step; `drain(slot)`
+        collects the last step.  lag = 0: the gathered records of this very step (what a collective gives)."""
         import os
         self.world, self.rank, self.dist, self.n_slots = world, rank, dist, n_slots
         self.device = torch.device(device)
         self.rec_shape = tuple(rec_shape)
         self.rec_floats = (int(rec_shape[0] * rec_shape[1]) + 3) // 4 * 4
         self.timeout_s = timeout_s
+        self.lag = int(lag)
         mode = mode or os.environ.get("SB_GATHER", "peer")
         self.mode = "none" if world == 1 else ("nccl" if self.device.type != "cuda" else mode)
         self.note = ""
@@ -77,6 +81,8 @@ class RecordGather(object):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok[0]) == 0 and self.mode == "peer":
                 self.mode, self.note = "nccl", "a peer rank could not map the mailboxes, using nccl"
+        if self.mode != "peer":
+            self.lag = 0
         if self.mode == "nccl":
             self.groups = [dist.new_group() if self.device.type == "cuda" else None for _ in range(n_slots)]
 
@@ -133,7 +139,7 @@ class RecordGather(object):
             st = lib.stream_ptr()
             lib.check(L.sb_peer_put_record(lib.ptr(src), self._boxes, self.n_slots, self.world, self.rec_floats,
                                            self.rank, slot, st), "sb_peer_put_record")
-            lib.check(L.sb_peer_wait_records(self._own, self.n_slots, self.world, self.rec_floats, slot,
+            lib.check(L.sb_peer_wait_records(self._own, self.n_slots, self.world, self.rec_floats, slot, self.lag,
                                              lib.ptr(out), lib.ptr(self._err), float(self.timeout_s), st),
                       "sb_peer_wait_records")
             return out
@@ -141,9 +147,22 @@ class RecordGather(object):
                                          group=self.groups[slot])
         return out
 
+    def drain(self, slot):
+        """lag = 1: collect the records of the slot's LAST step (no new put) -> [world, R, C]; otherwise a no-op"""
+        if self.world == 1 or self.mode != "peer" or self.lag == 0:
+            return None if self.out is None else self.out[slot]
+        from . import lib
+        L = lib.load()
+        out = self.out[slot]
+        lib.check(L.sb_peer_wait_records(self._own, self.n_slots, self.world, self.rec_floats, slot, 0, lib.ptr(out),
+                                         lib.ptr(self._err), float(self.timeout_s), lib.stream_ptr()),
+                  "sb_peer_wait_records")
+        return out
+
     def describe(self):
         if self.world == 1:
             return "none (1 GPU)"
-        d = {"peer": "own kernels over NVLink peer memory (CUDA IPC mailboxes, posted 128-bit stores + release flags)",
+        d = {"peer": "own kernels over NVLink peer memory (CUDA IPC mailboxes, posted 128-bit stores + release flags%s)"
+                     % (", pipelined: a step collects the previous step's records" if self.lag else ""),
              "nccl": "ncclAllGather (torch.distributed.all_gather_into_tensor), one communicator per in-flight slot"}[self.mode]
         return d + ("; " + self.note if self.note else "")

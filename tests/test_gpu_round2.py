@@ -326,6 +326,22 @@ def _gather_worker(rank, world, port, mode, q):
                     g2 = torch.Generator().manual_seed(1000 * step + 10 * slot + r)
                     ok &= bool(torch.equal(out[r].cpu(), torch.rand(P.REC_ROIS, P.REC_COLS, generator=g2)))
         gat.check()
+        if mode == "peer":      # pipelined exchange (lag 1): a call returns the slot's PREVIOUS step, drain() the last one
+            gl = P.RecordGather(world, rank, dev, dist, n_slots=2, mode="peer", lag=1)
+            mk = lambda step, slot, r: torch.full((P.REC_ROIS, P.REC_COLS), float(1000 * step + 10 * slot + r))
+            for step in range(7):
+                for slot in range(2):
+                    out = gl(slot, mk(step, slot, rank).to(dev)).clone()
+                    torch.cuda.synchronize()
+                    if step > 0:
+                        for r in range(world):
+                            ok &= bool(torch.equal(out[r].cpu(), mk(step - 1, slot, r)))
+            for slot in range(2):
+                out = gl.drain(slot).clone()
+                torch.cuda.synchronize()
+                for r in range(world):
+                    ok &= bool(torch.equal(out[r].cpu(), mk(6, slot, r)))
+            gl.check()
         # shard equivalence: N ranks x 1 pair == 1 rank computing the same pairs (bit for bit)
         sd = make_state_dict(3)
         pipe = PL.StereoPipeline(sd, dev, throughput=True, scale=1.0)
