@@ -52,6 +52,7 @@ struct TcParams {
     int num_k_blocks;     // taps * kblocks_per_tap
     long long M;
     int pdl_late;         // fire griddepcontrol.launch_dependents after the last tile's MMAs instead of at entry
+    int cg2_direct;       // CTA pairs: the peer's TMA loads signal the LEADER's full barrier directly (no forwarding warp)
     unsigned long long* trace;   // optional per-CTA phase timestamps (sb_conv_trace), 16 words per CTA
 };
 
@@ -163,6 +164,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * kStageBytes;
                     uint8_t* sb = sa + kABytes;
+                    if (CG2 && p.cg2_direct) {
+                        // all four loads of the pair complete on the LEADER's barrier (patch mode only)
+                        const uint32_t lbar = mapa_rank(smem_u32(&full[stage]), 0);
+                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes);
+                        const int r = tap / d.kw, s = tap - r * d.kw;
+                        tma_load_4d_pair(&map_a, lbar, sa, c0, w0 + s - d.pad, h0 + r - d.pad, n_img);
+                        tma_load_2d_pair(&map_b, lbar, sb, tap * d.Cin + c0, nt * BLOCK_N + (int)crank * (BLOCK_N / 2));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full[stage], kStageBytes);
                     if (p.patch) {
                         const int r = tap / d.kw, s = tap - r * d.kw;
@@ -180,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===================== peer CTA: forward "stage full" to the leader =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tstep) {
+        for (int tile = tile0; tile < num_tiles && !p.cg2_direct; tile += tstep) {
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 mbar_wait(&full[stage], phase);                       // my A tile and my half of the weights have landed
                 if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(&pfull[stage]), 0));
@@ -203,8 +214,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                mbar_wait(&full[stage], phase);
-                if (CG2) mbar_wait_cluster(&pfull[stage], phase);
+                if (CG2 && p.cg2_direct) mbar_wait_cluster(&full[stage], phase);    // completed by both CTAs' loads
+                else mbar_wait(&full[stage], phase);
+                if (CG2 && !p.cg2_direct) mbar_wait_cluster(&pfull[stage], phase);
                 tc_fence_after();
                 if (tr && lane == 0 && kb == 0 && tile == tile0) { tr[2] = gtimer(); tr[10] = clock64(); }
                 if (elect_one()) {
@@ -1141,6 +1153,8 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     // next kernel's CTAs sit in griddepcontrol.wait on SMs the other stream's chain could be using
     static const bool pdl_late = getenv("SB_PDL_LATE") == nullptr || atoi(getenv("SB_PDL_LATE")) != 0;
     p.pdl_late = pdl_late ? 1 : 0;
+    static const bool cg2_direct = getenv("SB_CG2_DIRECT") != nullptr && atoi(getenv("SB_CG2_DIRECT")) != 0;
+    p.cg2_direct = cg2_direct ? 1 : 0;
     p.trace = nullptr;
     // spatial 8x16 tiles for 3x3 convs, and for the FPN laterals so that the bilinear upsample taps of a tile
     // (5x9 source pixels) stay in L1 instead of being re-fetched from L2 for every output row

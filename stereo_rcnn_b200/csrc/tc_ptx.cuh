@@ -192,6 +192,22 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                  : "memory");
 }
+// TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the completion is signalled on a barrier
+// that may live in EITHER CTA of the pair (bar_cluster_addr: a shared::cluster address, e.g. mapa_rank(.., 0))
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* smem, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
 // instruction descriptor of the pair's MMA: M = 256 (128 rows per CTA)
 __host__ __device__ constexpr uint32_t make_idesc_2cta(int n, bool f16) {
     return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) |
