@@ -1153,7 +1153,10 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
     // next kernel's CTAs sit in griddepcontrol.wait on SMs the other stream's chain could be using
     static const bool pdl_late = getenv("SB_PDL_LATE") == nullptr || atoi(getenv("SB_PDL_LATE")) != 0;
     p.pdl_late = pdl_late ? 1 : 0;
-    static const bool cg2_direct = getenv("SB_CG2_DIRECT") != nullptr && atoi(getenv("SB_CG2_DIRECT")) != 0;
+    // default: both CTAs' TMA loads complete on the leader's barrier (cta_group::2 TMA).  SB_CG2_DIRECT=0 selects the
+    // first protocol tried -- the peer's warp 1 forwards "stage full" with a remote mbarrier arrive -- which is correct
+    // but 1.7x slower (415 us for the RPN P2 conv: the extra hop sits on the operand ring's round trip).
+    static const bool cg2_direct = getenv("SB_CG2_DIRECT") == nullptr || atoi(getenv("SB_CG2_DIRECT")) != 0;
     p.cg2_direct = cg2_direct ? 1 : 0;
     p.trace = nullptr;
     // spatial 8x16 tiles for 3x3 convs, and for the FPN laterals so that the bilinear upsample taps of a tile
@@ -1189,8 +1192,10 @@ extern "C" int sb_conv2d_tc(const sb_conv_desc* d, sb_stream_t stream) {
         flat = (BN == 32 && d->out && !d->out16 && !d->residual) || (BN == 64 && f16only) || BN == 128 || (BN == 256 && f16only);
     }
     p.num_n_tiles = (d->Cout + BN - 1) / BN;
-    // CTA pairs (cta_group::2) for the 256-wide 3x3 convs: opt-in until verified (SB_TC_CG2=1)
-    static const bool cg2_on = getenv("SB_TC_CG2") != nullptr && atoi(getenv("SB_TC_CG2")) != 0;
+    // CTA pairs (cta_group::2) for the 256-wide 3x3 convs (default on; SB_TC_CG2=0 switches back to single-CTA tiles).
+    // Measured on B200 (tools/conv_trace.py): RPN P2 conv 245 -> 229 us (1.43 -> 1.54 PFLOP/s), all 3x3 convs of a
+    // forward 1022 -> 958 us of SM time; bench +1..3 %.
+    static const bool cg2_on = getenv("SB_TC_CG2") == nullptr || atoi(getenv("SB_TC_CG2")) != 0;
     const bool cg2 = cg2_on && !flat && !small && f16 && p.patch && d->kh == 3 && !d->up_src && !d->residual && BN == 256 &&
                      d->Cout % 256 == 0 && p.num_m_tiles >= 2;
     if (g_trace && g_trace_n < g_trace_cap) {
