@@ -8,8 +8,8 @@
 //   seq   [n_slots]                                   this rank's own step counter per slot (device-resident, so
 //                                                     that put/wait can be captured into a CUDA graph and replayed)
 //
-// put  : one CTA stores the local record into every peer's mailbox with 128-bit stores over NVLink (P2P writes
-//        are posted: no round trip), fences at system scope, then releases the peer's flag.  40 KB per peer.
+// put  : CTA p stores the local record into rank p's mailbox with 128-bit stores over NVLink (P2P writes are
+//        posted: no round trip), fences at system scope, then releases that peer's flag.  40 KB per peer.
 // wait : CTA q acquires flag (slot, q) of the LOCAL mailbox, then copies rank q's record out of the mailbox into
 //        the caller's gathered tensor.  The spin is bounded (%globaltimer) so that a lost peer cannot hang the GPU.
 //
@@ -52,35 +52,37 @@ struct Layout {
     }
     __host__ __device__ size_t flag_off(int slot, int r) const { return (size_t)slot * world + r; }   // in u32 after data
     __host__ __device__ size_t seq_off(int slot) const { return (size_t)n_slots * world + slot; }
-    __host__ __device__ size_t bytes() const { return data_floats() * 4 + ((size_t)n_slots * world + n_slots) * 4 + 64; }
+    __host__ __device__ size_t ticket_off(int slot) const { return (size_t)n_slots * world + n_slots + slot; }
+    __host__ __device__ size_t bytes() const { return data_floats() * 4 + ((size_t)n_slots * world + 2 * n_slots) * 4 + 64; }
 };
 
-__global__ void __launch_bounds__(1024)
+// grid = world CTAs of 256 threads (small enough to co-reside with the 225 KB / 320-thread conv CTAs that fill the
+// SMs): CTA p writes the record into rank p's mailbox.  Every CTA reads the slot's step counter before the last one
+// to finish (ticket) advances it.
+__global__ void __launch_bounds__(256)
 peer_put_kernel(const float* __restrict__ rec, PeerPtrs peers, Layout L, int rank, int slot) {
     unsigned* my_ctl = reinterpret_cast<unsigned*>(peers.p[rank] + L.data_floats());
-    __shared__ unsigned s_seq;
-    if (threadIdx.x == 0) {
-        s_seq = my_ctl[L.seq_off(slot)] + 1u;
-        my_ctl[L.seq_off(slot)] = s_seq;
-    }
-    __syncthreads();
-    const unsigned seq = s_seq;
+    const int p = blockIdx.x;
+    const unsigned seq = my_ctl[L.seq_off(slot)] + 1u;
     const int par = (int)(seq % kParities);
     const int n4 = L.rec_floats / 4;
     const float4* src = reinterpret_cast<const float4*>(rec);
-    for (int p = 0; p < L.world; ++p) {
-        float4* dst = reinterpret_cast<float4*>(peers.p[p] + L.data_off(slot, par, rank));
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
-    }
+    float4* dst = reinterpret_cast<float4*>(peers.p[p] + L.data_off(slot, par, rank));
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
     __threadfence_system();
     __syncthreads();
-    if ((int)threadIdx.x < L.world) {
-        unsigned* ctl = reinterpret_cast<unsigned*>(peers.p[threadIdx.x] + L.data_floats());
+    if (threadIdx.x == 0) {
+        unsigned* ctl = reinterpret_cast<unsigned*>(peers.p[p] + L.data_floats());
         st_release_sys(ctl + L.flag_off(slot, rank), seq);
+        if (atomicAdd(&my_ctl[L.ticket_off(slot)], 1u) == (unsigned)L.world - 1u) {      // last CTA of this put
+            my_ctl[L.ticket_off(slot)] = 0u;
+            __threadfence();
+            my_ctl[L.seq_off(slot)] = seq;
+        }
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 peer_wait_kernel(float* __restrict__ mailbox, Layout L, int slot, int lag, float* __restrict__ out, int* __restrict__ err,
                  unsigned long long timeout_ns) {
     const int q = blockIdx.x;
@@ -155,7 +157,7 @@ extern "C" int sb_peer_put_record(const float* rec, void* const* mailboxes, int 
         return SB_EINVAL;
     PeerPtrs pp;
     for (int i = 0; i < kMaxPeers; ++i) pp.p[i] = i < world ? static_cast<float*>(mailboxes[i]) : nullptr;
-    peer_put_kernel<<<1, 1024, 0, sb_cs(stream)>>>(rec, pp, make_layout(n_slots, world, rec_floats), rank, slot);
+    peer_put_kernel<<<world, 256, 0, sb_cs(stream)>>>(rec, pp, make_layout(n_slots, world, rec_floats), rank, slot);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;
@@ -166,7 +168,7 @@ extern "C" int sb_peer_wait_records(void* mailbox, int n_slots, int world, int r
     if (!mailbox || !gathered || !err_flag || world < 1 || world > kMaxPeers || slot < 0 || slot >= n_slots || lag < 0 || lag > 1 ||
         rec_floats < 4 || (rec_floats & 3) || (reinterpret_cast<uintptr_t>(gathered) & 15))
         return SB_EINVAL;
-    peer_wait_kernel<<<world, 256, 0, sb_cs(stream)>>>(static_cast<float*>(mailbox), make_layout(n_slots, world, rec_floats),
+    peer_wait_kernel<<<world, 128, 0, sb_cs(stream)>>>(static_cast<float*>(mailbox), make_layout(n_slots, world, rec_floats),
                                                        slot, lag, gathered, err_flag,
                                                        (unsigned long long)(timeout_s * 1e9));
     SB_LAUNCHED();

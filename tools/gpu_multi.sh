@@ -12,8 +12,10 @@ timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q --timeout 150 -k 
 fi
 echo "== gather + shard equivalence tests ($N GPUs visible)"
 timeout 600 python -m pytest tests/test_gpu_round2.py -m gpu -q --timeout 500 -s -k "record_gather" > $out/pytest_multi_$N.log 2>&1; echo "rc=$?"; tail -6 $out/pytest_multi_$N.log
+if [ -n "$WITH_LAG0" ]; then
 echo "== bench N=$N, peer gather, same-step (lag 0)"
 timeout 400 $T bench.py --gpus $N --steps 20 --warmup 5 --gather peer --gather-lag 0 > $out/bench_n${N}_peer0.json 2> $out/bench_n${N}_peer0.err; echo "rc=$?"; tail -c 200 $out/bench_n${N}_peer0.err
+fi
 echo "== bench N=$N, peer gather, pipelined (default)"
 timeout 400 $T bench.py --gpus $N --steps 20 --warmup 5 --gather peer > $out/bench_n${N}_peer.json 2> $out/bench_n${N}_peer.err; echo "rc=$?"; tail -c 300 $out/bench_n${N}_peer.err
 echo "== bench N=$N, nccl gather"
