@@ -139,8 +139,8 @@ def run_ours(args):
     pipe_lat = pipeline.StereoPipeline(sd, dev, scale=SCALE)             # one pair at a time: lowest latency
     pipe = pipeline.StereoPipeline(sd, dev, throughput=True, scale=SCALE) if (n_inflight > 1 or MB > 1) else pipe_lat
     copy_stream = torch.cuda.Stream(device=dev)
-    # peer mode runs the exchange pipelined (lag 1): a step puts its record and collects the previous step's, so no
-    # rank waits for a slower peer's current step; the last step of every slot is drained inside the timed region
+    # peer mode (opt-in) runs the exchange pipelined (lag 1): a step puts its record and collects the previous step's, so
+    # no rank waits for a slower peer's current step; the last step of every slot is drained inside the timed region
     gather = parallel.RecordGather(world, rank, dev, dist, n_slots=n_inflight + 1, mode=args.gather,
                                    rec_shape=(MB * N_ROIS, REC_COLS), lag=args.gather_lag)
 
@@ -675,7 +675,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default=None, choices=[None, "peer", "nccl"],
-                    help="record exchange at N>1: own peer-memory kernels (default) or ncclAllGather")
+                    help="record exchange at N>1: ncclAllGather on per-slot communicators (default, measured faster) or "
+                         "own kernels over NVLink peer memory")
     ap.add_argument("--microbatch", type=int, default=int(os.environ.get("SB_MICROBATCH", "1")),
                     help="pairs per step of one in-flight slot, batched through every launch (M-batching)")
     ap.add_argument("--gather-lag", type=int, default=int(os.environ.get("SB_GATHER_LAG", "1")), choices=[0, 1],
