@@ -620,8 +620,11 @@ struct FlatParams {
 
 constexpr int flat_epi_warp_bytes(bool res, bool f32) { return f32 ? ((res ? 3 : 2) * 4096 + 4096) : 4096; }
 
+constexpr int kStemGatherWarps = 8;       // 2 threads per A-tile row: each builds 4 of the 8 16-byte groups of a K-step
+constexpr int kStemThreads = 320 + 32 * kStemGatherWarps;
+
 template <int BLOCK_N, int kStages, bool HAS_RES, bool F32, bool STEM = false>
-__global__ void __launch_bounds__(STEM ? 448 : 320, 1)
+__global__ void __launch_bounds__(STEM ? kStemThreads : 320, 1)
 conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_o32,
                     const __grid_constant__ CUtensorMap map_o16, const FlatParams p) {
@@ -660,9 +663,9 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     if (warp == 1) {
         if (elect_one()) {
-            // STEM: a stage is full when the weight tile has landed (1 expect_tx arrival) and the 128 gather threads
+            // STEM: a stage is full when the weight tile has landed (1 expect_tx arrival) and the gather threads
             // have written their patch rows
-            for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], STEM ? 129 : 1); mbar_init(&empty[i], 1); }
+            for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], STEM ? 1 + 32 * kStemGatherWarps : 1); mbar_init(&empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
             for (int i = 0; i < 24; ++i) mbar_init(&rfull[i], 1);
             fence_barrier_init();
@@ -731,20 +734,26 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (p.pdl_late) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         if (tr && lane == 0) { tr[3] = gtimer(); tr[11] = clock64(); }
     } else if (STEM && warp >= 10) {
-        // ===================== stem patch gather (warps 10..13) =====================
-        // The 7x7 / stride-2 / pad-3 stem convolution (resnet.py:111) as an implicit GEMM: thread gt builds row gt of
-        // the A tile -- the 147 taps (ci, r, s) of its output pixel, zero padded to 3 K-steps of 64 fp16 -- straight
-        // from the NCHW fp32 image into the 128-byte-swizzled stage (16-byte group j of row r at j ^ (r & 7)), so the
-        // 229 MB patch matrix of round 1 (sb_stem_im2col16) is never written or read.  Image reads hit L1 / L2: every
-        // input pixel is used by ~12 taps of neighbouring outputs.
+        // ===================== stem patch gather (warps 10..17) =====================
+        // The 7x7 / stride-2 / pad-3 stem convolution (resnet.py:111) as an implicit GEMM: row gr of the A tile holds
+        // the 147 taps (ci, r, s) of one output pixel, zero padded to 3 K-steps of 64 fp16, built straight from the
+        // NCHW fp32 image into the 128-byte-swizzled stage (16-byte group j of row r at j ^ (r & 7)), so the 229 MB
+        // patch matrix of round 1 (sb_stem_im2col16) is never written or read.  Image reads hit L1 / L2: every input
+        // pixel is used by ~12 taps of neighbouring outputs.  Two threads build a row (4 groups each per K-step); all
+        // loads of a K-step are issued before the first use and before the wait for the stage, so a thread exposes
+        // the load latency once per K-step, not once per tap (4x faster than load-convert-store per group; measured).
+        // Variants that were measured and lost (profiles/r02f_stem_fused.md): rows padded to 8 columns and loaded as
+        // 8-byte words, one barrier arrival per warp, L1 prefetch of the CTA's next tile.
+        constexpr int kPer = 8 / (kStemGatherWarps / 4);       // 16-byte groups per thread and K-step
         const int gt = threadIdx.x - 320;
+        const int gr = gt & 127, gh = gt >> 7;
         int stage = 0;
         uint32_t phase = 0;
         const int H = p.sH, W = p.sW;
         const long long HW = (long long)H * W;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / p.num_n_tiles;
-            const long long m = (long long)mt * BLOCK_M + gt;
+            const long long m = (long long)mt * BLOCK_M + gr;
             const bool valid = m < p.M;
             int n = 0, ho = 0, wo = 0;
             if (valid) {
@@ -755,32 +764,47 @@ conv_tc_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 wo = rem - ho * p.sWo;
             }
             const int y0 = 2 * ho - 3, x0 = 2 * wo - 3;
-            const float* base = p.stem_im + (long long)n * 3 * HW + (long long)y0 * W + x0;
+            const float* img = p.stem_im + (long long)n * 3 * HW;
+            const float* base = img + (long long)y0 * W + x0;
             const bool interior = valid && y0 >= 0 && y0 + 6 < H && x0 >= 0 && x0 + 6 < W;
 #pragma unroll
             for (int kb = 0; kb < 3; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                const uint32_t row = smem_u32(smem + stage * kStageBytes) + gt * 128;
+                float v[kPer * 8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int g = 0; g < kStemGatherWarps / 4; ++g) {          // g == gh: keeps every tap index a constant
+                    if (g != gh) continue;
+                    if (interior) {
+#pragma unroll
+                        for (int i = 0; i < kPer * 8; ++i) {
+                            const int k = kb * 64 + g * kPer * 8 + i;
+                            const int ci = k / 49, r = (k % 49) / 7, sx = k % 7;
+                            v[i] = k < 147 ? __ldg(base + ci * HW + r * W + sx) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPer * 8; ++i) {
+                            const int k = kb * 64 + g * kPer * 8 + i;
+                            const int ci = k / 49, r = (k % 49) / 7, sx = k % 7;
+                            const int yy = y0 + r, xx = x0 + sx;
+                            const bool ok = valid && k < 147 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+                            const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+                            const float t = __ldg(img + (k < 147 ? ci : 0) * HW + (long long)yc * W + xc);   // always in bounds
+                            v[i] = ok ? t : 0.f;
+                        }
+                    }
+                }
+                mbar_wait(&empty[stage], phase ^ 1);
+                const uint32_t row = smem_u32(smem + stage * kStageBytes) + gr * 128;
+#pragma unroll
+                for (int jj = 0; jj < kPer; ++jj) {
+                    const int j = gh * kPer + jj;
                     uint32_t h[4];
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
-                        float v[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int k = kb * 64 + 8 * j + 2 * e2 + e;       // compile-time after unrolling
-                            v[e] = 0.f;
-                            if (k < 147) {
-                                const int ci = k / 49, r = (k % 49) / 7, sx = k % 7;
-                                const bool ok = interior || (valid && y0 + r >= 0 && y0 + r < H && x0 + sx >= 0 && x0 + sx < W);
-                                if (ok) v[e] = __ldg(base + ci * HW + r * W + sx);
-                            }
-                        }
-                        __half2 pk = __floats2half2_rn(v[0], v[1]);
+                        __half2 pk = __floats2half2_rn(v[jj * 8 + 2 * e2], v[jj * 8 + 2 * e2 + 1]);
                         h[e2] = *reinterpret_cast<uint32_t*>(&pk);
                     }
-                    sts128u(row + ((uint32_t)(j ^ (gt & 7)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+                    sts128u(row + ((uint32_t)(j ^ (gr & 7)) << 4), make_uint4(h[0], h[1], h[2], h[3]));
                 }
                 fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&full[stage]);
@@ -1066,7 +1090,7 @@ int launch_flat(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     static const bool use_pdl = getenv("SB_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(STEM ? 448 : 320);
+    cfg.blockDim = dim3(STEM ? kStemThreads : 320);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];

@@ -50,7 +50,7 @@ class StereoRCNNEngine(object):
         self.precision = "fp32-simt" if conv_impl == "simt" else precision
         self.keep32 = False
         self.chain_ctas = int(os.environ.get("SB_CHAIN_CTAS", "0"))
-        self.stem_fused = os.environ.get("SB_STEM_FUSED", "0") != "0"
+        self.stem_fused = os.environ.get("SB_STEM_FUSED", "1") != "0"
         self.rpn_streams = os.environ.get("SB_RPN_STREAMS", "1") != "0"
         self.head_streams = os.environ.get("SB_HEAD_STREAMS", "1") != "0"
         # lr_streams: run layers 3-4 of the left and the right image as two concurrent chains (lowest latency of a
@@ -97,6 +97,7 @@ class StereoRCNNEngine(object):
         wst = torch.zeros(64, 192, 1, 1)                              # fp16 variant: three 64-wide K-steps
         wst[:, :147, 0, 0] = sd["RCNN_layer0.0.weight"].reshape(64, 147)
         self.p["stem_gemm16"] = PackedConv(wst, s, b, 0)
+        self.stem_w16 = ops.pack_stem_w16(sd["RCNN_layer0.0.weight"])   # K layout of the fused (implicit-GEMM) stem
         for li, nb in enumerate(LAYERS):
             for bi in range(nb):
                 p = "RCNN_layer%d.0.%d" % (li + 1, bi)
@@ -137,6 +138,7 @@ class StereoRCNNEngine(object):
         for pc in list(self.p.values()) + [c for row in self.deconv for c in row]:
             pc.w, pc.w16, pc.scale, pc.shift = mv(pc.w), mv(pc.w16), mv(pc.scale), mv(pc.shift)
         self.stem = tuple(mv(t) for t in self.stem)
+        self.stem_w16 = mv(self.stem_w16)
         self.kpts_class = tuple(mv(t) for t in self.kpts_class)
         self.fc = [mv(t) for t in self.fc]
 
@@ -229,7 +231,7 @@ class StereoRCNNEngine(object):
         (residual adds, FPN upsample source, RoIAlign, the user-visible P levels)."""
         if self.stem_fused:     # patches gathered inside the GEMM kernel: no 229 MB patch matrix
             pc = self.p["stem_gemm16"]
-            c0 = ops.stem_conv_tc(im_nchw, pc.w16.view(64, 192), pc.scale, pc.shift)
+            c0 = ops.stem_conv_tc(im_nchw, self.stem_w16, pc.scale, pc.shift)
             self.impl_used["stem"] = "tc16-fused"
         else:
             c0 = self._conv(ops.stem_im2col16(im_nchw), self.p["stem_gemm16"], relu=True, tag="stem", f32=False, f16=True)

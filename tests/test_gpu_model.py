@@ -219,6 +219,32 @@ def test_stem_maxpool_subsample():
     np.testing.assert_array_equal(ss.cpu().numpy(), mp[:, ::2, ::2].cpu().numpy())
 
 
+@pytest.mark.parametrize("shape", [(2, 67, 102), (1, 40, 77), (3, 7, 8), (1, 130, 260)])
+def test_stem_conv_tc_fused_gather(shape):
+    """the stem as an implicit tensor-core GEMM (patches gathered inside the kernel, no patch matrix): against the
+    convolution (resnet.py:111-113) of the SAME fp16-rounded image and weights in fp64 -- what the tensor core computes
+    up to fp32 accumulation order and the fp16 rounding of the result -- on even widths (8-byte loads), odd widths
+    (scalar path), borders everywhere (7x8) and several images / partial last tile"""
+    N, H, W = shape
+    sd = OM.make_state_dict(3)
+    g = torch.Generator().manual_seed(N * 1000 + W)
+    im = torch.randn(N, 3, H, W, generator=g) * 50
+    s = sd["RCNN_layer0.1.weight"] / torch.sqrt(sd["RCNN_layer0.1.running_var"] + 1e-5)
+    b = sd["RCNN_layer0.1.bias"] - sd["RCNN_layer0.1.running_mean"] * s
+    w16 = G.pack_stem_w16(sd["RCNN_layer0.0.weight"])
+    y = G.stem_conv_tc(cu(im), cu(w16), cu(s), cu(b))
+    assert y.shape == (N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64) and y.dtype == torch.float16
+    conv = F.conv2d(im.half().double(), sd["RCNN_layer0.0.weight"].half().double(), stride=2, padding=3)
+    ref = F.relu(conv * s.double().view(1, -1, 1, 1) + b.double().view(1, -1, 1, 1))
+    got = y.permute(0, 3, 1, 2).double().cpu()
+    # fp16 output: half an ulp (2^-11 relative) per element + fp32 accumulation noise
+    assert ((got - ref).abs() <= 6e-4 * ref.abs() + 2e-5 * float(ref.abs().max())).all()
+    assert l2_err(got, ref) < 4e-4
+    # and against the unrounded fp32 convolution at the path's operand bar
+    ref32 = F.relu(OM._bn(OM._conv(im, sd, "RCNN_layer0.0", stride=2, pad=3), sd, "RCNN_layer0.1"))
+    assert l2_err(got.float(), ref32) < 1e-3
+
+
 def test_head_tails_and_decode():
     sd = OM.make_state_dict(3)
     g = torch.Generator().manual_seed(1)
