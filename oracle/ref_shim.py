@@ -185,6 +185,34 @@ def load():
     return _loaded
 
 
+_loaded_train = None
+
+
+def load_train():
+    """the reference's REAL train-time target layers (anchor_target_layer.py, proposal_target_layer.py), exec'd on CPU
+    with py2 -> py3 / torch 0.3 -> 2.x text patches only (`long(` -> `int(`, the removed `Tensor.index`, implicit
+    relative imports); `load()` keeps stubs under the module names because the eval-mode model never calls them."""
+    global _loaded_train
+    if _loaded_train is not None:
+        return _loaded_train
+    ref = load()
+    torch.cuda.LongTensor = torch.LongTensor
+    atl = _exec_module("model.rpn._anchor_target_layer_real", os.path.join(LIB, "model/rpn/anchor_target_layer.py"), [
+        ("from generate_anchors import", "from model.rpn.generate_anchors import"),
+        ("from bbox_transform import", "from model.rpn.bbox_transform import"),
+        ("long(im_info[0][1])", "int(im_info[0][1])"),
+        ("long(im_info[0][0])", "int(im_info[0][0])"),
+    ])
+    ptl = _exec_module("model.rpn._proposal_target_layer_real", os.path.join(LIB, "model/rpn/proposal_target_layer.py"), [
+        ("from ..utils.config import cfg", "from model.utils.config import cfg"),
+        ("from bbox_transform import", "from model.rpn.bbox_transform import"),
+        (".contiguous().view(-1).index(offset.view(-1))", ".contiguous().view(-1)[offset.view(-1)]"),
+    ])
+    _loaded_train = types.SimpleNamespace(cfg=ref.cfg, anchor_target_layer=atl, proposal_target_layer=ptl,
+                                          net_utils=ref.net_utils, generate_anchors=ref.generate_anchors)
+    return _loaded_train
+
+
 class Calib(object):
     """minimal stand-in for kitti_utils.FrameCalibrationData (only p2/p3 are read)"""
 

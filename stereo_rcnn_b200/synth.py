@@ -198,3 +198,60 @@ def make_reference_init_state_dict(seed=3, n_classes=2):
             t = torch.randn(shp, generator=g) * std
         sd[k] = t.float().contiguous()
     return sd
+
+
+def synth_train_gt(B, K, H, W, seed, n_boxes=None, disparity=6.0):
+    """ground truth of a training batch in the layout of roibatchLoader.py:199-240: gt_left / gt_right / gt_merge
+    [B,K,5] (x1, y1, x2, y2, class; zero rows pad to K = MAX_NUM_GT_BOXES), gt_dim_orien [B,K,5], gt_kpts [B,K,6]
+    (four perspective keypoints, one visible, -1 otherwise; left / right border), all fp32"""
+    rng = np.random.RandomState(seed)
+    n_boxes = n_boxes or [min(K, 3 + 2 * b) for b in range(B)]
+    gl = np.zeros((B, K, 5), np.float32)
+    for b in range(B):
+        for j in range(n_boxes[b]):
+            w = rng.uniform(0.08 * W, 0.35 * W)
+            h = rng.uniform(0.1 * H, 0.4 * H)
+            x1 = rng.uniform(disparity + 2, W - w - 1)
+            y1 = rng.uniform(0, H - h - 1)
+            gl[b, j] = [x1, y1, x1 + w, y1 + h, 1]
+    gr = gl.copy()
+    gr[:, :, 0] -= disparity
+    gr[:, :, 2] -= disparity
+    gr[gl[:, :, 4] == 0] = 0
+    gm = gl.copy()
+    gm[:, :, 0] = np.minimum(gl[:, :, 0], gr[:, :, 0])
+    gm[:, :, 2] = np.maximum(gl[:, :, 2], gr[:, :, 2])
+    dim = rng.uniform(-1, 4, (B, K, 5)).astype(np.float32)
+    kp = np.zeros((B, K, 6), np.float32)
+    for b in range(B):
+        for j in range(K):
+            x1, x2 = gl[b, j, 0], gl[b, j, 2]
+            kp[b, j, :4] = -1
+            kp[b, j, rng.randint(4)] = rng.uniform(x1, x2)
+            kp[b, j, 4] = rng.uniform(x1, x1 + 0.3 * (x2 - x1))
+            kp[b, j, 5] = rng.uniform(x2 - 0.3 * (x2 - x1), x2)
+    return gl, gr.astype(np.float32), gm.astype(np.float32), dim, kp, np.asarray(n_boxes, np.int64)
+
+
+def synth_train_rois(gt_left, R, H, W, seed, near_gt=0.34, jitter=6.0, disparity=6.0):
+    """proposals of a training step: a fraction `near_gt` jittered copies of ground-truth boxes (foreground
+    candidates), the rest uniform boxes -> rois_left, rois_right [B,R,5] (batch index first)"""
+    rng = np.random.RandomState(seed)
+    B = gt_left.shape[0]
+    out = np.zeros((B, R, 5), np.float32)
+    for b in range(B):
+        n = int((gt_left[b, :, 4] > 0).sum())
+        for r in range(R):
+            if n > 0 and rng.uniform() < near_gt:
+                out[b, r, 1:] = gt_left[b, rng.randint(n), :4] + rng.uniform(-jitter, jitter, 4)
+            else:
+                w = rng.uniform(0.04 * W, 0.4 * W)
+                h = rng.uniform(0.06 * H, 0.5 * H)
+                x1 = rng.uniform(disparity, W - w - 1)
+                y1 = rng.uniform(0, H - h - 1)
+                out[b, r, 1:] = [x1, y1, x1 + w, y1 + h]
+        out[b, :, 0] = b
+    right = out.copy()
+    right[:, :, 1] -= disparity
+    right[:, :, 3] -= disparity
+    return out, right

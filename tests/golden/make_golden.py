@@ -129,6 +129,56 @@ def solver_goldens():
     print("solver goldens written")
 
 
+def train_goldens():
+    """(11) train-time target layers (A16): the reference's OWN `_AnchorTargetLayer` / `_ProposalTargetLayer` /
+    `_smooth_l1_loss` run on CPU (oracle/ref_shim.load_train: text patches only) with numpy's global stream seeded as
+    trainval_net.py does (np.random.seed(cfg.RNG_SEED) = 3).  Inputs come from stereo_rcnn_b200.synth generators
+    (recorded by their arguments; the arrays are stored too, the fixture is self-contained)."""
+    from stereo_rcnn_b200 import synth
+    ref = ref_shim.load_train()
+    cfg = ref.cfg
+    t = torch.from_numpy
+    out = {}
+    H, W = 160, 256
+    feat_shapes = [[int(np.ceil(H / s)), int(np.ceil(W / s))] for s in (4, 8, 16, 32, 64)]
+    out["feat_shapes"] = np.asarray(feat_shapes)
+    for case, (B, batchsize, seed) in {"a": (2, 512, 0), "b": (3, 32, 5)}.items():
+        gl, gr, gm, dim, kp, nb = synth.synth_train_gt(B, 30, H, W, seed)
+        im_info = np.array([[H, W, 1.6]] * B, np.float32)
+        cfg.TRAIN.RPN_BATCHSIZE = batchsize
+        layer = ref.anchor_target_layer._AnchorTargetLayer(1, cfg.ANCHOR_RATIOS)
+        np.random.seed(3)
+        res = layer((torch.zeros(B, 2, 1, 1), t(gl), t(gr), t(gm), t(im_info), t(nb), feat_shapes))
+        cfg.TRAIN.RPN_BATCHSIZE = 512
+        out.update({"at_%s_gt_left" % case: gl, "at_%s_gt_right" % case: gr, "at_%s_gt_merge" % case: gm,
+                    "at_%s_im_info" % case: im_info, "at_%s_rpn_batchsize" % case: batchsize})
+        for nm, r in zip(("labels", "targets_left", "targets_right", "inside_w", "outside_w"), res):
+            out["at_%s_%s" % (case, nm)] = r.numpy()
+        lab = res[0].numpy()
+        print("anchor targets", case, "fg", (lab == 1).sum(1), "bg", (lab == 0).sum(1))
+    names = ("rois_left", "rois_right", "labels", "bbox_targets_left", "bbox_targets_right", "dim_orien_targets",
+             "kpts_targets", "kpts_weight", "inside_w", "outside_w")
+    for case, (B, R, near, seed) in {"a": (2, 200, 0.34, 1), "b": (2, 700, 0.6, 2)}.items():
+        gl, gr, gm, dim, kp, nb = synth.synth_train_gt(B, 30, H, W, seed)
+        rl, rr = synth.synth_train_rois(gl, R, H, W, seed + 100, near_gt=near)
+        layer = ref.proposal_target_layer._ProposalTargetLayer(2)
+        np.random.seed(3)
+        res = layer(t(rl), t(rr), t(gl), t(gr), t(dim), t(kp), t(nb))
+        out.update({"pt_%s_in_rois_left" % case: rl, "pt_%s_in_rois_right" % case: rr, "pt_%s_gt_left" % case: gl,
+                    "pt_%s_gt_right" % case: gr, "pt_%s_gt_dim_orien" % case: dim, "pt_%s_gt_kpts" % case: kp})
+        for nm, r in zip(names, res):
+            out["pt_%s_%s" % (case, nm)] = r.numpy()
+        print("proposal targets", case, "fg", (res[2].numpy() > 0).sum(1))
+    g = torch.Generator().manual_seed(0)
+    pred, tgt = torch.randn(3, 40, 6, generator=g), torch.randn(3, 40, 6, generator=g) * 0.5
+    iw = (torch.rand(3, 40, 6, generator=g) > 0.5).float()
+    ow = torch.rand(3, 40, 6, generator=g)
+    out.update(sl1_pred=pred.numpy(), sl1_target=tgt.numpy(), sl1_inside=iw.numpy(), sl1_outside=ow.numpy(),
+               sl1_sigma3=float(ref.net_utils._smooth_l1_loss(pred, tgt, iw, ow, sigma=3, dim=[1])),
+               sl1_plain=float(ref.net_utils._smooth_l1_loss(pred[0], tgt[0])))
+    np.savez_compressed(os.path.join(HERE, "train_targets.npz"), **out)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "demo":
         return demo_goldens()
@@ -265,6 +315,7 @@ def main():
                         cls_dets_left=ns2["cls_dets_left"].numpy(), cls_kpts=ns2["cls_kpts"].numpy())
     demo_goldens()
     solver_goldens()
+    train_goldens()
     print("goldens written to", HERE)
 
 
