@@ -265,6 +265,85 @@ int sb_peer_put_record(const float* rec, void* const* mailboxes, int n_slots, in
 int sb_peer_wait_records(void* mailbox, int n_slots, int world, int rec_floats, int slot, int lag, float* gathered,
                          int* err_flag, double timeout_s, sb_stream_t stream);
 
+/* ------------------------------------------------- train-time target layers and losses ----
+ * The label / target assignment and the losses of one training step on the device, no host round trip.
+ * Every compare is bit-identical to the reference (fp32, same operation order); the regression targets differ at most
+ * in the last ulp of log().  The random sampler takes explicit words instead of numpy's global stream (which the
+ * reference consumes with data-dependent lengths): see oracle/train_targets.py (NumpySampler / KeySampler).
+ *
+ * sb_anchor_targets -- _AnchorTargetLayer.forward (lib/model/rpn/anchor_target_layer.py:42-164):
+ *   anchors [A,4] fp32 (all pyramid levels, the proposal layer's order), gt_left / gt_right / gt_merge [B,K,5]
+ *   (x1, y1, x2, y2, class; zero rows pad to K <= 64), im_h / im_w = int(im_info[0][0..1]) (image 0 bounds the anchors
+ *   of the whole batch, :70-73), keys [B,A] uint32: one random word per anchor -- when an image has more than
+ *   num_fg foreground (or more than rpn_batchsize - n_fg background) anchors, those with the SMALLEST (key, index)
+ *   are disabled, i.e. "the first n - keep of a random permutation" (:109-123).
+ *   -> labels [B,A] (1 / 0 / -1), targets_left / targets_right [B,A,4] (bbox_transform_batch, bbox_transform.py:38-77;
+ *   zeros outside the image), inside_w / outside_w [B,A] (outside = 1 / #sampled anchors of the LAST image, :136).
+ * sb_proposal_targets -- _ProposalTargetLayer.forward (lib/model/rpn/proposal_target_layer.py:36-333):
+ *   rois_left / rois_right [B,R,5] (batch index first), gt_* as above, gt_dim_orien [B,K,5], gt_kpts [B,K,6];
+ *   keys [B,R+K] (one word per candidate incl. the appended ground-truth boxes: foreground = the fg_rois_per_image
+ *   candidates with the smallest (key, index), in that order), words [B,S] (background draw j = candidate
+ *   words[j] * n_bg >> 32, i.e. floor(u * n_bg) with u = words[j] / 2^32; also the with-replacement draws of the
+ *   one-sided cases :249-265) -> S = rois_per_image rows per image: rois, labels, box targets (normalised),
+ *   dimension / orientation targets, keypoint / border bin targets (int32) and weights, inside / outside weights,
+ *   keep_inds (index into the R+K candidates) and status [B] (1 = neither foreground nor background, the
+ *   reference's ValueError :267).  R + K <= 4096, S <= 1024.
+ * sb_rpn_loss -- stereo_rpn.py:114-140: losses[0] = cross entropy over the anchors with label != -1, losses[1] =
+ *   _smooth_l1_loss (net_utils.py:79-99, sigma 3) on the 6-d deltas; optional gradients w.r.t. rpn_cls_score [B,A,2] and
+ *   rpn_bbox_pred [B,A,6] (both or neither), scaled by exp(-uncert[0..1]) when uncert != NULL.
+ * sb_rcnn_loss -- stereo_rcnn.py:201-311: losses[0..3] = RCNN_loss_cls, RCNN_loss_bbox, RCNN_loss_dim_orien,
+ *   RCNN_loss_kpts; bbox_pred [R,6C] / dim_orien_pred [R,5C] are the per-class outputs (gathered by label inside);
+ *   optional gradients w.r.t. all six prediction tensors (all or none), scaled by exp(-uncert[2..5]).
+ * sb_multitask_loss -- trainval_net.py:214-219: total = sum_i losses[i] exp(-uncert[i]) + uncert[i]; d_uncert optional.
+ * sb_clip_gradient -- net_utils.clip_gradient (net_utils.py:37-49) over n_tensors gradient tensors (HOST arrays of
+ *   device pointers / element counts): one global norm, one scale; norm_out [2] (device) = total norm, applied factor.
+ * Reductions are two-level in a fixed order: deterministic.                                                     */
+typedef struct sb_proposal_target_cfg {
+    int rois_per_image;        /* cfg.TRAIN.BATCH_SIZE = 512                         */
+    int fg_rois_per_image;     /* round(FG_FRACTION * BATCH_SIZE) = 128              */
+    float fg_thresh;           /* 0.5                                                */
+    float bg_thresh_hi;        /* 0.5                                                */
+    float bg_thresh_lo;        /* 0.0                                                */
+    float bbox_means[4];       /* BBOX_NORMALIZE_MEANS (0, 0, 0, 0)                  */
+    float bbox_stds[4];        /* BBOX_NORMALIZE_STDS (0.1, 0.1, 0.2, 0.2)           */
+    float dim_means[5];        /* DIM_NORMALIZE_MEANS (1.6, 1.5, 4.0, 0, 0)          */
+    float dim_stds[5];         /* DIM_NORMALIZE_STDS (0.5 x 5)                       */
+    int kpts_grid;             /* cfg.KPTS_GRID = 28                                 */
+} sb_proposal_target_cfg;
+
+size_t sb_anchor_targets_workspace(int B, int A);
+int sb_anchor_targets(const float* anchors, int A, const float* gt_left, const float* gt_right,
+                      const float* gt_merge, int B, int K, int im_h, int im_w, const unsigned* keys,
+                      float neg_overlap, float pos_overlap, int rpn_batchsize, int num_fg, void* workspace,
+                      size_t workspace_bytes, float* labels, float* targets_left, float* targets_right,
+                      float* inside_w, float* outside_w, sb_stream_t stream);
+int sb_proposal_targets(const float* rois_left, const float* rois_right, int B, int R, const float* gt_left,
+                        const float* gt_right, const float* gt_dim_orien, const float* gt_kpts, int K,
+                        const unsigned* keys, const unsigned* words, const sb_proposal_target_cfg* cfg,
+                        float* out_rois_left, float* out_rois_right, float* labels, float* bbox_targets_left,
+                        float* bbox_targets_right, float* dim_orien_targets, int* kpts_targets,
+                        float* kpts_weight, float* inside_w, float* outside_w, int* keep_inds, int* status,
+                        sb_stream_t stream);
+size_t sb_loss_workspace_bytes(void);
+int sb_rpn_loss(const float* rpn_cls_score, const float* rpn_bbox_pred, const float* labels,
+                const float* targets_left, const float* targets_right, const float* inside_w,
+                const float* outside_w, int B, int A, const float* uncert, void* workspace,
+                size_t workspace_bytes, float* losses, float* d_cls_score, float* d_bbox_pred,
+                sb_stream_t stream);
+int sb_rcnn_loss(const float* cls_score, const float* bbox_pred, const float* dim_orien_pred,
+                 const float* kpts_pred, const float* left_border_pred, const float* right_border_pred,
+                 const float* labels, const float* bbox_targets_left, const float* bbox_targets_right,
+                 const float* dim_orien_targets, const int* kpts_targets, const float* kpts_weight,
+                 const float* inside_w, const float* outside_w, int R, int n_classes, int kpts_grid,
+                 const float* uncert, float* losses, float* d_cls_score, float* d_bbox_pred,
+                 float* d_dim_orien_pred, float* d_kpts_pred, float* d_left_border_pred,
+                 float* d_right_border_pred, sb_stream_t stream);
+int sb_multitask_loss(const float* losses, const float* uncert, int n, float* total, float* d_uncert,
+                      sb_stream_t stream);
+size_t sb_clip_gradient_workspace(int n_tensors);
+int sb_clip_gradient(float* const* grads, const size_t* counts, int n_tensors, float clip_norm,
+                     void* workspace, size_t workspace_bytes, float* norm_out, sb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,13 @@ class ConvDesc(ctypes.Structure):
                 ("out16", c_void_p), ("in_dtype", c_int), ("max_ctas", c_int)]
 
 
+class ProposalTargetCfg(ctypes.Structure):
+    _fields_ = [("rois_per_image", c_int), ("fg_rois_per_image", c_int), ("fg_thresh", c_float),
+                ("bg_thresh_hi", c_float), ("bg_thresh_lo", c_float), ("bbox_means", c_float * 4),
+                ("bbox_stds", c_float * 4), ("dim_means", c_float * 5), ("dim_stds", c_float * 5),
+                ("kpts_grid", c_int)]
+
+
 _SIGS = {
     "sb_version": (c_int, []),
     "sb_device_cc": (c_int, []),
@@ -96,6 +103,20 @@ _SIGS = {
     "sb_ipc_close": (c_int, [c_void_p]),
     "sb_peer_put_record": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sb_peer_wait_records": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p]),
+    # train-time target layers and losses (A16)
+    "sb_anchor_targets_workspace": (c_size_t, [c_int, c_int]),
+    "sb_anchor_targets": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_float, c_float, c_int, c_int, c_void_p, c_size_t] + [c_void_p] * 5 + [c_void_p]),
+    "sb_proposal_targets": (c_int, [c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 4 + [c_int, c_void_p, c_void_p,
+                                    ctypes.POINTER(ProposalTargetCfg)] + [c_void_p] * 12 + [c_void_p]),
+    "sb_loss_workspace_bytes": (c_size_t, []),
+    "sb_rpn_loss": (c_int, [c_void_p] * 7 + [c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
+    "sb_rcnn_loss": (c_int, [c_void_p] * 14 + [c_int, c_int, c_int] + [c_void_p] * 8 + [c_void_p]),
+    "sb_multitask_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "sb_clip_gradient_workspace": (c_size_t, [c_int]),
+    "sb_clip_gradient": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_int, c_float, c_void_p, c_size_t,
+                                 c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)
