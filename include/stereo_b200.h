@@ -93,6 +93,10 @@ int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_lr, const fl
                       int B, int A, const sb_proposal_cfg* cfg,
                       float* rois_left, float* rois_right,
                       void* workspace, size_t workspace_bytes, sb_stream_t stream);
+/* the whole anchor table of the pyramid (generate_anchors.py:112-173: fp64, cast to fp32), [A,4] in the proposal
+ * layer's order (level, y, x, ratio); only shapes / anchor_scales / feat_strides / ratios of cfg are read.  The
+ * proposal layer itself never materialises it; the train-time anchor target layer (below) needs it. */
+int sb_generate_anchors(const sb_proposal_cfg* cfg, int A, float* anchors, sb_stream_t stream);
 /* fused RPN head epilogue: raw head output [B, sum(h*w), ld] (cols 0..5 cls logits in the
  * reference's channel order, 6..23 the 18 box channels) -> cls_prob [B,A,2], bbox_pred [B,A,6]
  * with the reference's softmax channel pairing (stereo_rpn.py:52-60,81-83)               */

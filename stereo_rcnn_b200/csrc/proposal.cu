@@ -361,7 +361,55 @@ WsLayout ws_layout(int A, int K) {
     return w;
 }
 
+// generate_anchors.py:112-173 for every anchor of the pyramid (the train-time target layer needs the whole table; the
+// proposal layer only decodes the survivors): fp64 centre -/+ 0.5 * size, cast to fp32 (`.type_as(scores)`)
+__global__ void __launch_bounds__(256)
+anchors_kernel(AnchorCfg cfg, int A, float4* __restrict__ out) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= A) return;
+    int l = 0;
+    while (l + 1 < cfg.n_levels && idx >= cfg.start[l + 1]) ++l;
+    const int r0 = idx - cfg.start[l];
+    const int ratio = r0 % cfg.n_ratios;
+    const int cell = r0 / cfg.n_ratios;
+    const int x = cell % cfg.width[l], y = cell / cfg.width[l];
+    const double cx = (double)(x * cfg.stride[l]), cy = (double)(y * cfg.stride[l]);
+    const double hw = 0.5 * cfg.aw[l][ratio], hh = 0.5 * cfg.ah[l][ratio];
+    out[idx] = make_float4((float)(cx - hw), (float)(cy - hh), (float)(cx + hw), (float)(cy + hh));
+}
+
+int make_anchor_cfg(const sb_proposal_cfg* pc, AnchorCfg* ac) {
+    ac->n_levels = pc->n_levels;
+    ac->n_ratios = pc->n_ratios;
+    int tot = 0;
+    for (int l = 0; l < pc->n_levels; ++l) {
+        ac->start[l] = tot;
+        ac->width[l] = pc->shapes[l][1];
+        ac->stride[l] = pc->feat_strides[l];
+        tot += pc->shapes[l][0] * pc->shapes[l][1] * pc->n_ratios;
+        for (int r = 0; r < pc->n_ratios; ++r) {
+            // generate_anchors.py:122-128: heights = scales / sqrt(ratios), widths = scales * sqrt(ratios)
+            ac->aw[l][r] = (double)pc->anchor_scales[l] * sqrt(pc->ratios[r]);
+            ac->ah[l][r] = (double)pc->anchor_scales[l] / sqrt(pc->ratios[r]);
+        }
+    }
+    ac->start[pc->n_levels] = tot;
+    return tot;
+}
+
 }  // namespace
+
+extern "C" int sb_generate_anchors(const sb_proposal_cfg* pc, int A, float* anchors, sb_stream_t stream) {
+    if (!pc || !anchors || pc->n_levels < 1 || pc->n_levels > kMaxLevels || pc->n_ratios < 1 || pc->n_ratios > kMaxRatios ||
+        (reinterpret_cast<uintptr_t>(anchors) & 15))
+        return SB_EINVAL;
+    AnchorCfg ac;
+    if (make_anchor_cfg(pc, &ac) != A) return SB_EINVAL;
+    anchors_kernel<<<sb_div_up(A, 256), 256, 0, sb_cs(stream)>>>(ac, A, reinterpret_cast<float4*>(anchors));
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
 
 extern "C" size_t sb_proposal_workspace_bytes(int B, int A, int pre_nms_top_n) {
     (void)B;
@@ -376,21 +424,7 @@ extern "C" int sb_proposal_layer(const float* cls_prob, const float* bbox_pred_l
     if (!pc || pc->n_levels < 1 || pc->n_levels > kMaxLevels || pc->n_ratios < 1 || pc->n_ratios > kMaxRatios)
         return SB_EINVAL;
     AnchorCfg ac;
-    ac.n_levels = pc->n_levels;
-    ac.n_ratios = pc->n_ratios;
-    int tot = 0;
-    for (int l = 0; l < pc->n_levels; ++l) {
-        ac.start[l] = tot;
-        ac.width[l] = pc->shapes[l][1];
-        ac.stride[l] = pc->feat_strides[l];
-        tot += pc->shapes[l][0] * pc->shapes[l][1] * pc->n_ratios;
-        for (int r = 0; r < pc->n_ratios; ++r) {
-            // generate_anchors.py:122-128: heights = scales / sqrt(ratios), widths = scales * sqrt(ratios)
-            ac.aw[l][r] = (double)pc->anchor_scales[l] * sqrt(pc->ratios[r]);
-            ac.ah[l][r] = (double)pc->anchor_scales[l] / sqrt(pc->ratios[r]);
-        }
-    }
-    ac.start[pc->n_levels] = tot;
+    const int tot = make_anchor_cfg(pc, &ac);
     if (tot != A || B < 0) return SB_EINVAL;
     const int K = (pc->pre_nms_top_n > 0 && pc->pre_nms_top_n < A) ? pc->pre_nms_top_n : A;
     const int post_n = pc->post_nms_top_n > 0 ? pc->post_nms_top_n : K;

@@ -100,6 +100,9 @@ at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __rest
     for (int k = threadIdx.x; k < K; k += blockDim.x) s_max[k] = 0u;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned ovk[kMaxGt];                                        // ordered overlap per gt box; 0 = not a candidate
+#pragma unroll
+    for (int k = 0; k < kMaxGt; ++k) ovk[k] = 0u;
     if (i < A) {
         const float4 a = anchors[i];
         float best = -1.f;
@@ -110,16 +113,27 @@ at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __rest
             const bool azero = ax == 1.f && ay == 1.f;
             best = -INFINITY;
             arg = 0;
-            for (int k = 0; k < K; ++k) {
-                float ov = overlap(a, aarea, s.box[k], s.area[k]);
-                if (s.zero[k]) ov = 0.f;
-                if (azero) ov = -1.f;
-                if (ov > best) { best = ov; arg = k; }
-                atomicMax(&s_max[k], f2ord(ov));
+#pragma unroll
+            for (int k = 0; k < kMaxGt; ++k) {                  // unrolled: ovk[] stays in registers
+                if (k < K) {
+                    float ov = overlap(a, aarea, s.box[k], s.area[k]);
+                    if (s.zero[k]) ov = 0.f;
+                    if (azero) ov = -1.f;
+                    if (ov > best) { best = ov; arg = k; }
+                    ovk[k] = f2ord(ov);
+                }
             }
         }
         max_ov[(size_t)b * A + i] = best;
         arg_ov[(size_t)b * A + i] = arg;                         // -1: outside the image
+    }
+    // per-gt maximum: warp reduction, one shared atomic per warp and box, one global atomic per CTA and box
+#pragma unroll
+    for (int k = 0; k < kMaxGt; ++k) {
+        if (k < K) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, ovk[k]);
+            if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[k], m);
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x)
@@ -176,12 +190,13 @@ at_label_kernel(const float4* __restrict__ anchors, int A, const float* __restri
 // first n - keep entries of a random permutation of the candidates" = disable the n - keep candidates with the
 // smallest (key, index): a 4-pass radix select on the key, ties at the threshold resolved in index order.
 constexpr int kSelThreads = 1024;
+constexpr int kSelUnroll = 8;
 
 __global__ void __launch_bounds__(kSelThreads)
 at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, int A, const int* __restrict__ counts,
                  int rpn_batch, int num_fg) {
     __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ unsigned s_prefix, s_remaining, s_bucket;
     __shared__ int s_scan[kSelThreads / 32];
     __shared__ int s_base;
     const int b = blockIdx.x, side = blockIdx.y;
@@ -203,8 +218,19 @@ at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, 
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < A; i += blockDim.x)
-            if (lab[i] == mine && (key[i] & mask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+        for (int base = 0; base < A; base += kSelThreads * kSelUnroll) {      // kSelUnroll independent loads in flight
+            float lv[kSelUnroll];
+            unsigned kv[kSelUnroll];
+#pragma unroll
+            for (int u = 0; u < kSelUnroll; ++u) {
+                const int i = base + u * kSelThreads + threadIdx.x;
+                lv[u] = i < A ? lab[i] : -2.f;
+                kv[u] = i < A ? key[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kSelUnroll; ++u)
+                if (lv[u] == mine && (kv[u] & mask) == prefix) atomicAdd(&hist[(kv[u] >> shift) & 255u], 1u);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned acc = 0, digit = 0;
@@ -214,6 +240,7 @@ at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, 
             }
             s_prefix = prefix | (digit << shift);
             s_remaining = d - acc;                                          // rank inside the chosen bucket
+            s_bucket = hist[digit];                                         // after the last pass: #candidates with key == T
         }
         __syncthreads();
         prefix = s_prefix;
@@ -223,12 +250,27 @@ at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, 
     }
     // prefix == T; d == how many candidates with key == T are disabled (the first d by index)
     const unsigned T = prefix;
+    const bool all_eq = d == s_bucket;            // every candidate with key == T goes (the usual case: keys are unique)
+    for (int base = 0; base < A; base += kSelThreads * kSelUnroll) {
+        float lv[kSelUnroll];
+        unsigned kv[kSelUnroll];
+#pragma unroll
+        for (int u = 0; u < kSelUnroll; ++u) {
+            const int i = base + u * kSelThreads + threadIdx.x;
+            lv[u] = i < A ? lab[i] : -2.f;
+            kv[u] = i < A ? key[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kSelUnroll; ++u)
+            if (lv[u] == mine && (kv[u] < T || (all_eq && kv[u] == T))) lab[base + u * kSelThreads + threadIdx.x] = -1.f;
+    }
+    if (all_eq) return;                                                     // CTA-uniform
+    // a tie at the threshold: of the candidates with key == T the first d by index go -- ordered pass
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int start = 0; start < A; start += blockDim.x) {
         const int i = start + threadIdx.x;
-        const bool cand = i < A && lab[i] == mine;
-        const bool eq = cand && key[i] == T;
+        const bool eq = i < A && lab[i] == mine && key[i] == T;
         const unsigned bal = __ballot_sync(0xffffffffu, eq);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) s_scan[warp] = __popc(bal);
@@ -236,7 +278,7 @@ at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, 
         int before = s_base;
         for (int w = 0; w < warp; ++w) before += s_scan[w];
         const int rank = before + __popc(bal & ((1u << lane) - 1u));
-        if (cand && (key[i] < T || (eq && (unsigned)rank < d))) lab[i] = -1.f;
+        if (eq && (unsigned)rank < d) lab[i] = -1.f;
         __syncthreads();
         if (threadIdx.x == 0) {
             int tot = 0;
@@ -244,6 +286,7 @@ at_sample_kernel(float* __restrict__ labels, const unsigned* __restrict__ keys, 
             s_base += tot;
         }
         __syncthreads();
+        if ((unsigned)s_base >= d) break;                                   // CTA-uniform: all d found
     }
 }
 

@@ -59,6 +59,7 @@ _SIGS = {
     "sb_proposal_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sb_proposal_layer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(ProposalCfg),
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sb_generate_anchors": (c_int, [ctypes.POINTER(ProposalCfg), c_int, c_void_p, c_void_p]),
     "sb_rpn_head_epilogue": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "sb_dense_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "sb_dense_align": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_double), c_double,

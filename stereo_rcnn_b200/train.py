@@ -33,6 +33,17 @@ def _words(t):
     return t
 
 
+def generate_anchors(feat_shapes, device, ratios=None, scales=None, strides=None):
+    """generate_anchors_all_pyramids (generate_anchors.py:157-173) on the device -> [A,4] fp32"""
+    from .ops import make_proposal_cfg
+    L = _l.load()
+    pc = make_proposal_cfg("TRAIN", [list(map(int, s)) for s in feat_shapes], ratios=ratios, scales=scales, strides=strides)
+    A = sum(int(h) * int(w) for h, w in feat_shapes) * pc.n_ratios
+    out = torch.empty(A, 4, dtype=torch.float32, device=device)
+    check(L.sb_generate_anchors(ctypes.byref(pc), A, ptr(out), stream_ptr()), "sb_generate_anchors")
+    return out
+
+
 def anchor_targets(anchors, gt_left, gt_right, gt_merge, im_info, keys, cfg=CFG):
     """_AnchorTargetLayer.forward: anchors [A,4] fp32, gt_* [B,K,5], im_info = (H, W, ...) of image 0 as Python
     numbers, keys [B,A] int32 words -> labels [B,A], targets_left [B,A,4], targets_right [B,A,4], inside_w [B,A],

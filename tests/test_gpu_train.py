@@ -164,7 +164,7 @@ def test_multitask_loss_and_clip_gradient():
     total = T.multitask_loss([l for l in losses], uncert)
     total.backward()
     tot, d_u = G.multitask_loss(losses.detach().cuda(), uncert.detach().cuda())
-    assert abs(float(tot) - float(total)) <= 2e-6 * abs(float(total))
+    assert abs(float(tot) - float(total.detach())) <= 2e-6 * abs(float(total.detach()))
     np.testing.assert_allclose(d_u.cpu().numpy(), uncert.grad.numpy(), rtol=2e-6, atol=1e-7)
     g = torch.Generator().manual_seed(2)
     shapes = [(64, 3, 7, 7), (2048,), (1, ), (1024, 25088 // 16)] + [(17, 13)] * 60        # > one launch chunk
@@ -178,3 +178,39 @@ def test_multitask_loss_and_clip_gradient():
         assert (f < 1) == clipped
         for a, b in zip(dev, grads):
             np.testing.assert_allclose(a.cpu().numpy(), (b * np.float32(out[1])).numpy(), rtol=1e-6, atol=0)
+
+
+def test_drop_in_target_layers_and_device_anchors():
+    """the reference-facing modules (model.rpn.anchor_target_layer / proposal_target_layer signatures) and the device
+    anchor table (generate_anchors.py:112-173, bit-equal to the fp64 numpy table cast to fp32)"""
+    from stereo_rcnn_b200.model.rpn.anchor_target_layer import _AnchorTargetLayer
+    from stereo_rcnn_b200.model.rpn.proposal_target_layer import _ProposalTargetLayer
+    H, W, B = 600, 1987, 2
+    fs = feat_shapes(H, W)
+    anchors = G.generate_anchors(fs, "cuda")
+    np.testing.assert_array_equal(anchors.cpu().numpy(), O.anchors_all_pyramids(fs).astype(np.float32))
+    assert anchors.shape[0] == 298476
+    gl, gr, gm, dim, kp, nb = synth.synth_train_gt(B, 30, H, W, 4)
+    layer = _AnchorTargetLayer(1, [0.5, 1, 2])
+    layer.generator = torch.Generator(device="cuda").manual_seed(3)
+    im_info = torch.tensor([[H, W, 1.6]] * B)
+    out = layer((None, cu(gl), cu(gr), cu(gm), im_info, cu(nb), fs))
+    lab = out[0]
+    assert lab.shape == (B, 298476) and out[1].shape == (B, 298476, 4)
+    n_fg, n_bg = (lab == 1).sum(1), (lab == 0).sum(1)
+    assert (n_fg > 0).all() and (n_fg <= 256).all() and ((n_fg + n_bg) == 512).all()
+    # everything except the sampled subset is independent of the words: compare with the oracle's pre-sampling sets
+    keys0 = np.zeros((B, 298476), np.uint32)
+    ref = T.anchor_target_layer(anchors.cpu().numpy(), gl, gr, gm, im_info.numpy(), T.KeySampler(keys0))
+    for b in range(B):
+        fg_dev, fg_ref = lab[b].cpu().numpy() == 1, ref[0][b] == 1
+        assert (fg_dev == fg_ref).all() if fg_ref.sum() <= 256 else (fg_dev <= fg_ref).all()
+    np.testing.assert_allclose(out[1].cpu().numpy(), ref[1], rtol=0, atol=4e-7)
+    rl, rr = synth.synth_train_rois(gl, 2000, H, W, 5)
+    pl = _ProposalTargetLayer(2)
+    pl.generator = torch.Generator(device="cuda").manual_seed(4)
+    res = pl(cu(rl), cu(rr), cu(gl), cu(gr), cu(dim), cu(kp), cu(nb))
+    assert len(res) == 10 and res[0].shape == (B, 512, 5) and res[6].dtype == torch.int64
+    assert pl.status.cpu().tolist() == [0, 0]
+    assert ((res[2] > 0).sum(1) <= 128).all() and (res[2] > 0).sum() > 0
+    assert torch.equal(res[9], (res[8] > 0).float())
