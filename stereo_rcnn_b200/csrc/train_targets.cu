@@ -90,6 +90,7 @@ __device__ __forceinline__ bool anchor_inside(const float4 a, float im_w, float 
 
 // ------------------------------------------------------------------------------------------ anchor targets
 // pass 1: per inside anchor max / argmax overlap; per gt box the maximum over the inside anchors
+template <int KC>                                     // compile-time cap of K (32 covers cfg.MAX_NUM_GT_BOXES = 30)
 __global__ void __launch_bounds__(256)
 at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __restrict__ gt_merge, int K, float im_w,
                   float im_h, float* __restrict__ max_ov, int* __restrict__ arg_ov, unsigned* __restrict__ gt_max) {
@@ -100,9 +101,9 @@ at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __rest
     for (int k = threadIdx.x; k < K; k += blockDim.x) s_max[k] = 0u;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned ovk[kMaxGt];                                        // ordered overlap per gt box; 0 = not a candidate
+    unsigned ovk[KC];                                            // ordered overlap per gt box; 0 = not a candidate
 #pragma unroll
-    for (int k = 0; k < kMaxGt; ++k) ovk[k] = 0u;
+    for (int k = 0; k < KC; ++k) ovk[k] = 0u;
     if (i < A) {
         const float4 a = anchors[i];
         float best = -1.f;
@@ -114,7 +115,7 @@ at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __rest
             best = -INFINITY;
             arg = 0;
 #pragma unroll
-            for (int k = 0; k < kMaxGt; ++k) {                  // unrolled: ovk[] stays in registers
+            for (int k = 0; k < KC; ++k) {                      // unrolled: ovk[] stays in registers
                 if (k < K) {
                     float ov = overlap(a, aarea, s.box[k], s.area[k]);
                     if (s.zero[k]) ov = 0.f;
@@ -129,7 +130,7 @@ at_overlap_kernel(const float4* __restrict__ anchors, int A, const float* __rest
     }
     // per-gt maximum: warp reduction, one shared atomic per warp and box, one global atomic per CTA and box
 #pragma unroll
-    for (int k = 0; k < kMaxGt; ++k) {
+    for (int k = 0; k < KC; ++k) {
         if (k < K) {
             const unsigned m = __reduce_max_sync(0xffffffffu, ovk[k]);
             if ((threadIdx.x & 31) == 0 && m) atomicMax(&s_max[k], m);
@@ -568,7 +569,10 @@ extern "C" int sb_anchor_targets(const float* anchors, int A, const float* gt_le
     if (e != cudaSuccess) return (int)e;
     const float4* a4 = reinterpret_cast<const float4*>(anchors);
     const dim3 grid(sb_div_up(A, 256), B);
-    at_overlap_kernel<<<grid, 256, 0, st>>>(a4, A, gt_merge, K, (float)im_w, (float)im_h, max_ov, arg_ov, gt_max);
+    if (K <= 32)
+        at_overlap_kernel<32><<<grid, 256, 0, st>>>(a4, A, gt_merge, K, (float)im_w, (float)im_h, max_ov, arg_ov, gt_max);
+    else
+        at_overlap_kernel<kMaxGt><<<grid, 256, 0, st>>>(a4, A, gt_merge, K, (float)im_w, (float)im_h, max_ov, arg_ov, gt_max);
     SB_LAUNCHED();
     at_label_kernel<<<grid, 256, 0, st>>>(a4, A, gt_merge, K, max_ov, arg_ov, gt_max, neg_overlap, pos_overlap, labels,
                                           counts);

@@ -79,6 +79,19 @@ def test_proposal_targets_vs_oracle(R, near, seed):
         np.testing.assert_allclose(got[n].cpu().numpy(), ref[n], rtol=0, atol=4e-6, err_msg=n)
 
 
+def test_anchor_targets_more_than_32_gt_boxes():
+    """K = 40 ground-truth rows (the wide instance of the overlap kernel)"""
+    H, W, B = 160, 256, 2
+    anchors = O.anchors_all_pyramids(feat_shapes(H, W)).astype(np.float32)
+    gl, gr, gm, _dim, _kp, _nb = synth.synth_train_gt(B, 40, H, W, 21, n_boxes=[37, 40])
+    keys = words_np((B, anchors.shape[0]), 22)
+    ref = T.anchor_target_layer(anchors, gl, gr, gm, np.array([[H, W, 1.6]] * B, np.float32), T.KeySampler(keys))
+    got = G.anchor_targets(cu(anchors), cu(gl), cu(gr), cu(gm), (H, W), as_i32(keys))
+    np.testing.assert_array_equal(got[0].cpu().numpy(), ref[0])
+    np.testing.assert_array_equal(got[4].cpu().numpy(), ref[4])
+    np.testing.assert_allclose(got[1].cpu().numpy(), ref[1], rtol=0, atol=4e-7)
+
+
 def test_proposal_targets_no_candidates_sets_status():
     """no ground truth at all and zero-area proposals: neither foreground nor background (:267 raises)"""
     B, R = 1, 8
