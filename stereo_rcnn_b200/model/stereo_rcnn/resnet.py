@@ -4,8 +4,9 @@
 15-tuple result, so test_net.py / demo.py keep working.  The modules below only *hold* parameters;
 ``forward`` hands them to the sm_100a engine (stereo_rcnn_b200.engine) -- no torch.nn op runs.
 
-Training mode (trainval_net.py; target layers, losses, RoIAlign backward through the trunk) is the
-next row of the scope table and raises NotImplementedError here.
+Training mode (trainval_net.py) raises NotImplementedError here: the target layers, the losses and their gradients
+w.r.t. the network outputs exist on the device (stereo_rcnn_b200.train, model.rpn.anchor_target_layer /
+proposal_target_layer), the backward pass of the trunk and heads (dgrad / wgrad) does not.
 """
 import math
 
@@ -129,7 +130,8 @@ class resnet(nn.Module):
 
     def train(self, mode=True):
         if mode:
-            raise NotImplementedError("stereo_rcnn_b200: only the test-mode forward is built in this round")
+            raise NotImplementedError("stereo_rcnn_b200: no backward pass of the network (dgrad / wgrad); target layers and "
+                                      "losses are in stereo_rcnn_b200.train")
         return super().train(False)
 
     # ---------------------------------------------------------------- forward
