@@ -65,6 +65,14 @@ int sb_roi_align_backward(const float* top_grad, int N, int C, int H, int W,
                           const float* rois, int R, int ah, int aw, float spatial_scale,
                           float* bottom_grad, sb_stream_t stream);
 
+/* The same backward, deterministic: contributions are accumulated in 64-bit fixed point (scale from
+ * max|top_grad|, quantum max|top| * 2^-41), so the sums do not depend on the order of the atomics or of the RoIs --
+ * bit-identical run to run.  bottom_grad is OVERWRITTEN (no zero-fill needed); workspace = N*C*H*W*8 + 16 bytes. */
+size_t sb_roi_align_backward_det_workspace(int N, int C, int H, int W);
+int sb_roi_align_backward_det(const float* top_grad, int N, int C, int H, int W,
+                              const float* rois, int R, int ah, int aw, float spatial_scale,
+                              float* bottom_grad, void* workspace, size_t workspace_bytes, sb_stream_t stream);
+
 /* Fused PyramidRoI_Feat: level routing (Q14) + per-level scale (Q15) + tap lattice +
  * 2x2/stride-1 average, NHWC features, one launch for all levels.
  * feats[l]: N x H_l x W_l x C (l = P2..P5); out[r][ph][pw][out_coff + c], row pitch out_ld elements;

@@ -115,6 +115,61 @@ roi_align_bwd_nchw(const float* __restrict__ top, int C, int H, int W, const flo
     }
 }
 
+// ---- deterministic backward: the same scatter, accumulated in 64-bit FIXED POINT.  Integer addition is
+// associative, so the result does not depend on the order in which the atomics land (nor on the order of the RoIs):
+// bit-identical run to run, which the reference's float atomicAdds (roi_align_kernel.cu:132-139) are not.
+// Scale 2^e with e chosen from max|top_grad| so that 2^20 contributions of that magnitude cannot overflow 2^62: the
+// quantum is max|top| * 2^-41, far below fp32 resolution of the sum.
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+    unsigned m = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = __float_as_uint(x[i]) & 0x7fffffffu;        // |x| as bits: monotonic for finite / inf
+        m = b > m ? b : m;
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+__device__ __forceinline__ int fixed_exponent(unsigned absmax_bits) {
+    if (absmax_bits == 0u || absmax_bits >= 0x7f800000u) return 0;    // all zero, or inf / nan: nothing sensible to scale
+    int ex;
+    frexpf(__uint_as_float(absmax_bits), &ex);                         // |x| < 2^ex
+    return 41 - ex;                                                    // |x| * 2^e < 2^41; 2^20 of them < 2^61
+}
+
+__global__ void __launch_bounds__(256)
+roi_align_bwd_fixed_kernel(const float* __restrict__ top, int C, int H, int W, const float* __restrict__ rois, int ah,
+                           int aw, float scale, const unsigned* __restrict__ absmax,
+                           unsigned long long* __restrict__ acc) {
+    const int n = blockIdx.x;
+    const RoiGeom g = roi_geom(rois + 5 * n, scale, ah, aw);
+    const double s = ldexp(1.0, fixed_exponent(*absmax));
+    const int taps = ah * aw;
+    const int c0 = blockIdx.y * 32;
+    const int cend = min(c0 + 32, C);
+    for (int e = threadIdx.x; e < (cend - c0) * taps; e += blockDim.x) {
+        int c = c0 + e / taps, p = e % taps;
+        int ph = p / aw, pw = p % aw;
+        Tap t = make_tap(g, ph, pw, H, W);
+        if (t.zero) continue;
+        const double tv = (double)top[((size_t)n * C + c) * taps + p] * s;
+        unsigned long long* b = acc + (((size_t)g.batch * C + c) * H + t.h0) * W + t.w0;
+        atomicAdd(b, (unsigned long long)__double2ll_rn(tv * t.w00));         // two's complement: wraps like int64
+        atomicAdd(b + 1, (unsigned long long)__double2ll_rn(tv * t.w01));
+        atomicAdd(b + W, (unsigned long long)__double2ll_rn(tv * t.w10));
+        atomicAdd(b + W + 1, (unsigned long long)__double2ll_rn(tv * t.w11));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fixed_to_float_kernel(const unsigned long long* __restrict__ acc, size_t n, const unsigned* __restrict__ absmax,
+                      float* __restrict__ out) {
+    const double inv = ldexp(1.0, -fixed_exponent(*absmax));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)((double)(long long)acc[i] * inv);
+}
+
 struct PyramidArgs {
     const float* feat[4];
     int H[4], W[4];
@@ -238,6 +293,37 @@ extern "C" int sb_roi_align_backward(const float* top_grad, int N, int C, int H,
     if (R < 0 || C <= 0 || ah < 2 || aw < 2 || !top_grad || !rois || !bottom_grad) return SB_EINVAL;
     dim3 grid(R, (C + 31) / 32);
     roi_align_bwd_nchw<<<grid, 256, 0, sb_cs(stream)>>>(top_grad, C, H, W, rois, ah, aw, spatial_scale, bottom_grad);
+    SB_LAUNCHED();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" size_t sb_roi_align_backward_det_workspace(int N, int C, int H, int W) {
+    if (N < 1 || C < 1 || H < 2 || W < 2) return 0;
+    return (size_t)N * C * H * W * 8 + 16;
+}
+
+extern "C" int sb_roi_align_backward_det(const float* top_grad, int N, int C, int H, int W, const float* rois, int R,
+                                         int ah, int aw, float spatial_scale, float* bottom_grad, void* workspace,
+                                         size_t workspace_bytes, sb_stream_t stream) {
+    if (R < 0 || N < 1 || C <= 0 || H < 2 || W < 2 || ah < 2 || aw < 2 || !top_grad || !rois || !bottom_grad || !workspace ||
+        workspace_bytes < sb_roi_align_backward_det_workspace(N, C, H, W) || (reinterpret_cast<uintptr_t>(workspace) & 7))
+        return SB_EINVAL;
+    cudaStream_t st = sb_cs(stream);
+    const size_t n = (size_t)N * C * H * W;
+    unsigned long long* acc = static_cast<unsigned long long*>(workspace);
+    unsigned* absmax = reinterpret_cast<unsigned*>(acc + n);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, n * 8 + 16, st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t nt = (size_t)R * C * ah * aw;
+    if (R > 0) {
+        absmax_kernel<<<(int)((nt + 255) / 256 < 1184 ? (nt + 255) / 256 : 1184), 256, 0, st>>>(top_grad, nt, absmax);
+        SB_LAUNCHED();
+        dim3 grid(R, (C + 31) / 32);
+        roi_align_bwd_fixed_kernel<<<grid, 256, 0, st>>>(top_grad, C, H, W, rois, ah, aw, spatial_scale, absmax, acc);
+        SB_LAUNCHED();
+    }
+    fixed_to_float_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(acc, n, absmax, bottom_grad);
     SB_LAUNCHED();
     SB_CHECK_LAUNCH();
     return SB_OK;

@@ -53,6 +53,9 @@ _SIGS = {
                                      c_float, c_void_p, c_void_p]),
     "sb_roi_align_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                       c_float, c_void_p, c_void_p]),
+    "sb_roi_align_backward_det_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sb_roi_align_backward_det": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                          c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sb_roi_align_pyramid_nhwc": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                           c_int, c_float, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                           c_void_p]),

@@ -128,6 +128,18 @@ def roi_align_backward(ah, aw, scale, top_grad, rois, bottom_grad):
     return 1
 
 
+def roi_align_backward_det(ah, aw, scale, top_grad, rois, bottom_grad):
+    """deterministic RoIAlign backward (fixed-point accumulation): overwrites bottom_grad [N,C,H,W]"""
+    L = _l.load()
+    N, C, H, W = bottom_grad.shape
+    nbytes = L.sb_roi_align_backward_det_workspace(N, C, H, W)
+    ws = workspace(nbytes, bottom_grad.device, "roi_bwd_det")
+    check(L.sb_roi_align_backward_det(ptr(_f32c(top_grad)), N, C, H, W, ptr(_f32c(rois)), rois.shape[0], int(ah),
+                                      int(aw), float(scale), ptr(bottom_grad), ptr(ws), nbytes, stream_ptr()),
+          "sb_roi_align_backward_det")
+    return 1
+
+
 def roi_align_pyramid_nhwc(feats, im_h, rois, pooled, out=None, out_coff=0, round_tf32=False, half=False):
     """feats: 4 NHWC fp32 tensors (P2..P5); rois [R,5]; -> out [R,pooled,pooled,out_ld] NHWC (fp32, fp32 rounded
     to TF32, or fp16 when half=True)"""

@@ -160,6 +160,36 @@ def test_roi_align_backward_vs_oracle_and_autograd_module():
     assert f.grad is not None and torch.isfinite(f.grad).all()
 
 
+def test_roi_align_backward_deterministic_fixed_point():
+    """sb_roi_align_backward_det: same gradient as the atomic kernel / the oracle, but bit-identical run to run and
+    under any permutation of the RoIs (integer accumulation), also with heavily overlapping RoIs and a wide range"""
+    rs = np.random.RandomState(9)
+    feat_shape = (2, 24, 19, 63)
+    scale = np.float32(19 / 600.0)
+    rois = np.concatenate([rand_rois(60, 19, 63, 19 / 600.0, 5)] * 3)          # every pixel hit many times
+    rois[:, 0] = rs.randint(0, 2, rois.shape[0])
+    top = (rs.randn(rois.shape[0], 24, 8, 8) * np.exp(rs.uniform(-8, 8, (rois.shape[0], 1, 1, 1)))).astype(np.float32)
+    ref = np.zeros(feat_shape, np.float64)
+    for n in range(2):
+        sel = rois[:, 0] == n
+        r = rois[sel].copy()
+        r[:, 0] = 0
+        ref[n] = O.roi_align_backward(top[sel], r, (1,) + feat_shape[1:], 8, 8, scale)[0]
+    g = torch.full(feat_shape, 7.0, device="cuda")                               # overwritten, not accumulated
+    G.roi_align_backward_det(8, 8, scale, cu(top), cu(rois), g)
+    amax = np.abs(ref).max()
+    assert np.abs(g.cpu().numpy() - ref).max() <= 2e-5 * amax        # the oracle itself sums in fp32
+    perm = rs.permutation(rois.shape[0])
+    g2 = torch.empty(feat_shape, device="cuda")
+    G.roi_align_backward_det(8, 8, scale, cu(top[perm]), cu(rois[perm]), g2)
+    assert torch.equal(g, g2)
+    for _ in range(3):
+        G.roi_align_backward_det(8, 8, scale, cu(top), cu(rois), g2)
+        assert torch.equal(g, g2)
+    G.roi_align_backward_det(8, 8, scale, cu(np.zeros_like(top)), cu(rois), g2)
+    assert float(g2.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("pooled", [7, 14])
 def test_roi_align_pyramid_nhwc_vs_oracle(pooled):
     rs = np.random.RandomState(11)

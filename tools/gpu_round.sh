@@ -1,7 +1,13 @@
 #!/bin/bash
+# one GPU session: full gpu test suite, smoke, default bench (what the driver runs at round end) + train-stage timing
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q 2>&1 | tail -4
-timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base demangled -k regex:"at_|proposal_target|rpn_loss|rcnn_loss" -c 12 --csv --log-file $out/train_kernels.csv python tests/tools/train_targets_bench.py > $out/ncu_train.log 2>&1; echo "ncu rc=$?"
-grep -v "^==" $out/train_kernels.csv | grep duration | awk -F'","' '{print $5, $NF}' | cut -c1-120
+echo "== full gpu suite"
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+echo "== train-stage kernels"
+timeout 600 python tests/tools/train_targets_bench.py 2>&1 | tail -12
+echo "== bench (default)"
+timeout 900 python bench.py 2>&1 | tail -1 | tee $out/bench_final.json | cut -c1-300
