@@ -77,3 +77,54 @@ def test_world1_is_identity():
     rec = torch.rand(P.REC_ROIS, P.REC_COLS)
     assert torch.equal(P.gather_records(rec, 1)[0], rec)
     assert P.max_over_ranks(3.5, torch.device("cpu"), 1) == 3.5
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shapes = [(64, 3, 7, 7), (64,), (5, 3), (1000, 33), (7,)]
+        gb = P.GradientBuckets(shapes, "cpu", world, dist, bucket_bytes=40000)     # forces several buckets
+        assert [tuple(g.shape) for g in gb.grads] == shapes and len(gb.buckets) >= 3
+        assert all(g.data_ptr() % 16 == 0 for g in gb.grads)
+        for i, g in enumerate(gb.grads):
+            g.fill_(float(i + 1) * (rank + 1))                       # rank 0: i+1, rank 1: 2(i+1)
+        gb.all_reduce()
+        ok = all(torch.equal(g, torch.full_like(g, 1.5 * (i + 1))) for i, g in enumerate(gb.grads))
+        norm = gb.clip(10.0)
+        total = float(torch.sqrt(sum((torch.full(s, 1.5 * (i + 1)).double() ** 2).sum() for i, s in enumerate(shapes))))
+        ok = ok and abs(float(norm[0]) - total) < 1e-3 * total and abs(float(norm[1]) - 10.0 / total) < 1e-6
+        ok = ok and abs(float(gb.grads[0].flatten()[0]) - 1.5 * 10.0 / total) < 1e-6
+        losses = P.average_losses(torch.tensor([1.0, 2.0]) * (rank + 1), world, dist)
+        q.put((rank, ok, losses.tolist(), gb.describe()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_gradient_buckets():
+    """the training step's exchange: gradients as views into flat buckets, one all-reduce per bucket, averaged; global
+    norm clipping over the same views; loss averaging"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ok, losses, desc in res:
+        assert ok, (rank, desc)
+        assert losses == [1.5, 3.0]
+        assert "ncclAllReduce per bucket" in desc
+
+
+def test_gradient_buckets_single_rank_identity():
+    gb = P.GradientBuckets([(3, 4), (5,)], "cpu")
+    gb.grads[0].fill_(2.0)
+    gb.all_reduce()
+    assert float(gb.grads[0].sum()) == 24.0 and "single rank" in gb.describe()
+    gb.zero_()
+    assert float(gb.buckets[0].abs().sum()) == 0.0
