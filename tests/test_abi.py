@@ -47,6 +47,34 @@ def test_struct_layout_matches_c(so_path):
     assert ctypes.sizeof(ProposalCfg) == 4 + 64 + 32 + 32 + 4 + 32 + 4 + 4 + 4 + 4  # incl. 8-byte alignment pads
 
 
+def test_struct_layout_against_the_header_compiled_as_c(tmp_path):
+    """include/stereo_b200.h is plain C: compile it with gcc and compare sizeof / offsetof of every struct that crosses
+    the boundary with the ctypes mirrors field by field"""
+    import shutil
+    import subprocess
+    from stereo_rcnn_b200.lib import ConvDesc, ProposalCfg, ProposalTargetCfg
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"sb_conv_desc": ConvDesc, "sb_proposal_cfg": ProposalCfg, "sb_proposal_target_cfg": ProposalTargetCfg}
+    rename = {"in_": "in"}                                   # `in` is a Python keyword
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "stereo_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in cls._fields_:
+            fn = rename.get(f[0], f[0])
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f[0], cname, fn))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for f in cls._fields_:
+            assert int(got["%s.%s" % (cname, f[0])]) == getattr(cls, f[0]).offset, (cname, f[0])
+
+
 def test_no_oracle_import_in_product():
     """the product package and the measurement tools must never import the oracle (parity would be void); only
     tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU-baseline legs may"""
