@@ -1,7 +1,9 @@
 """``_AnchorTargetLayer`` with the reference's constructor and forward signature
-(lib/model/rpn/anchor_target_layer.py:26-164); the layer is four stream-ordered kernels behind one C-ABI call, no
-host synchronisation.  The random subsampling takes words from a torch generator on the device instead of numpy's
-global stream (see stereo_rcnn_b200/train.py)."""
+(lib/model/rpn/anchor_target_layer.py:26-164); the layer is four stream-ordered kernels behind one C-ABI call.  The
+random subsampling takes words from a torch generator on the device instead of numpy's global stream (see
+stereo_rcnn_b200/train.py).  Host synchronisation: none if `im_info` is a host tensor (as the data loader produces
+it); a CUDA `im_info` costs one 3-float read per call, because the image size is a launch argument -- callers that
+know (H, W) use `train.anchor_targets` directly."""
 import torch.nn as nn
 
 from stereo_rcnn_b200 import train as _train
